@@ -1,0 +1,184 @@
+/*
+ * nornic_knn.h — C ABI of libnornic_knn.so, the B200-native brute-force kNN engine that sits behind
+ * NornicDB's GPU boundary.
+ *
+ * Part 1 re-exports, symbol for symbol, the C functions of the cgo preamble in the reference's
+ * pkg/gpu/cuda/cuda_bridge.go (lines cited per function) so that file can link this library instead
+ * of carrying its own cuBLAS code (INTEGRATION.md shows the two-line change).  Part 2 is the fused,
+ * batched API the Go host calls after a one-function change in cuda.Device.Search.
+ *
+ * Conventions (same as the reference, cuda_bridge.go:20-33,452-453): int returns are 0 = ok, -1 =
+ * failure with a message retrievable through cuda_get_last_error() / nk_last_error(); pointer
+ * returns are NULL on failure.  Unlike the reference's process-global buffer, the message is
+ * thread-local.  Every entry point binds its CUDA device itself (cudaSetDevice per call), so
+ * callers may migrate between OS threads (goroutines) freely.  Host pointers are only borrowed for
+ * the duration of a call; every host-pointer entry point is synchronous.
+ *
+ * No torch / C++ types cross this boundary: plain pointers and sizes only.
+ */
+#ifndef NORNIC_KNN_H
+#define NORNIC_KNN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ======================================================================================
+ * Part 1 — legacy ABI (drop-in for the cgo preamble of pkg/gpu/cuda/cuda_bridge.go)
+ * ====================================================================================== */
+
+/* cuda_bridge.go:36-40.  Opaque to Go (only ever held as *C.CudaDevice).  The reference's struct
+ * carries a cuBLAS handle; this library has no cuBLAS dependency. */
+typedef struct CudaDevice CudaDevice;
+
+/* cuda_bridge.go:132-136.  Field layout kept identical (data, size in BYTES, memory_type). */
+typedef struct CudaBuffer {
+    float *data;
+    size_t size;
+    int memory_type; /* 0 = device, 1 = pinned host */
+} CudaBuffer;
+
+void cuda_set_error(const char *msg);  /* cuda_bridge.go:23 */
+const char *cuda_get_last_error(void); /* cuda_bridge.go:27 */
+void cuda_clear_error(void);           /* cuda_bridge.go:31 */
+
+int cuda_get_device_count(void);                     /* cuda_bridge.go:42  (-1 on error) */
+int cuda_is_available(void);                         /* cuda_bridge.go:52  (1/0) */
+CudaDevice *cuda_create_device(int device_id);       /* cuda_bridge.go:56  (NULL on error) */
+void cuda_release_device(CudaDevice *dev);           /* cuda_bridge.go:94  (NULL-safe) */
+const char *cuda_device_name(int device_id);         /* cuda_bridge.go:102 ("Unknown" on error) */
+size_t cuda_device_memory(int device_id);            /* cuda_bridge.go:113 (bytes, 0 on error) */
+int cuda_device_compute_capability(int device_id);   /* cuda_bridge.go:122 (major*10+minor; B200 = 100) */
+
+/* cuda_bridge.go:138.  count is in floats; host_data may be NULL (uninitialised buffer); the copy
+ * is synchronous.  memory_type 0 = device, 1 = pinned host. */
+CudaBuffer *cuda_create_buffer(CudaDevice *dev, float *host_data, size_t count, int memory_type);
+void cuda_release_buffer(CudaBuffer *buf);           /* cuda_bridge.go:184 (NULL-safe) */
+void *cuda_buffer_data(CudaBuffer *buf);             /* cuda_bridge.go:197 */
+size_t cuda_buffer_size(CudaBuffer *buf);            /* cuda_bridge.go:201 */
+/* cuda_bridge.go:205.  Copies min(count*4, size) bytes; 0 / -1. */
+int cuda_buffer_copy_to_host(CudaBuffer *buf, float *host_data, size_t count);
+
+/* cuda_bridge.go:231.  norms[i] = ||vectors[i]||2.  One kernel (the reference issues n cublasSnrm2 calls). */
+int cuda_compute_norms(CudaDevice *dev, CudaBuffer *vectors, CudaBuffer *norms, unsigned int n, unsigned int dims);
+/* cuda_bridge.go:249.  In place; rows with norm <= 1e-10 are left untouched (cuda_bridge.go:267). */
+int cuda_normalize_vectors(CudaDevice *dev, CudaBuffer *vectors, unsigned int n, unsigned int dims);
+/* cuda_bridge.go:290.  scores[i] = embeddings[i] . query when normalized != 0 (what the reference's
+ * sgemv computes for every input, cuda_bridge.go:293-309); when normalized == 0 the true cosine
+ * dot/(|e||q|) with 0 for zero vectors (the case the reference leaves as a TODO). */
+int cuda_cosine_similarity(CudaDevice *dev, CudaBuffer *embeddings, CudaBuffer *query, CudaBuffer *scores,
+                           unsigned int n, unsigned int dims, int normalized);
+/* cuda_bridge.go:327.  out_indices/out_scores are HOST arrays of length k; k is clamped to n; result
+ * sorted by score descending, ties by lowest index first (the strict '>' forward scan of
+ * cuda_bridge.go:356-371).  Selection runs on the device; only k pairs cross PCIe. */
+int cuda_topk(CudaDevice *dev, CudaBuffer *scores, unsigned int *out_indices, float *out_scores, unsigned int n,
+              unsigned int k);
+
+/* ======================================================================================
+ * Part 2 — fused batched kNN API (what cuda.Device.Search / gpu.EmbeddingIndex call instead of
+ * NewBuffer + CosineSimilarity + TopK)
+ * ====================================================================================== */
+
+/* Metric enum = vectorspace.DistanceMetric, pkg/vectorspace/registry.go:27-31. */
+enum { NK_METRIC_COSINE = 0, NK_METRIC_DOT = 1, NK_METRIC_EUCLIDEAN = 2 };
+/* Corpus element type held in HBM.  Queries and scores are always fp32. */
+enum { NK_DTYPE_F32 = 0, NK_DTYPE_F16 = 1 };
+/* Kernel selection for nk_index_set_path (diagnostics / tests); AUTO picks by Q, dim and dtype. */
+enum { NK_PATH_AUTO = 0, NK_PATH_SIMT = 1, NK_PATH_TENSOR = 2 };
+
+#define NK_MAX_K 1024u
+
+typedef struct NkIndex NkIndex;
+
+typedef struct NkStats {
+    uint64_t rows;            /* total rows resident */
+    uint64_t searches;        /* nk_search* calls */
+    uint64_t queries;         /* queries answered */
+    uint64_t kernel_launches; /* kernels launched by this index */
+    uint64_t bytes_h2d;       /* host->device bytes moved by this index */
+    uint64_t bytes_d2h;
+    uint64_t bytes_scanned;   /* corpus bytes streamed from HBM by search kernels */
+    uint32_t n_devices;
+    uint32_t dim;
+} NkStats;
+
+const char *nk_last_error(void);
+const char *nk_version(void);
+
+/* An index = one row-major [N x dim] corpus, row-sharded by contiguous ranges over n_devices GPUs of
+ * this process (shard g holds rows [base_g, base_g + n_g)).  gpu.EmbeddingIndex storage, gpu.go:1224-1260. */
+NkIndex *nk_index_create(const int *device_ids, int n_devices, uint32_t dim, int dtype, int metric);
+void nk_index_release(NkIndex *ix); /* NULL-safe */
+
+/* Replace the corpus with n_rows host rows (dtype of the index), split evenly over the devices.
+ * Replaces syncToCUDA's NewBuffer + NormalizeVectors (gpu.go:2073-2118): rows are stored RAW; cosine
+ * normalisation happens inside the search kernel, so device rows always equal host rows. */
+int nk_index_upload(NkIndex *ix, const void *rows_host, uint64_t n_rows);
+/* Append rows to the last shard without re-uploading the rest (EmbeddingIndex.Add, gpu.go:1378-1434). */
+int nk_index_append(NkIndex *ix, const void *rows_host, uint64_t n_rows);
+/* Overwrite row `row` (global index) in place (EmbeddingIndex.Add on an existing id, gpu.go:1391-1399). */
+int nk_index_update_row(NkIndex *ix, uint64_t row, const void *row_host);
+/* Swap-with-last removal (EmbeddingIndex.Remove, gpu.go:1437-1471): row `row` takes the contents of the
+ * last row and the corpus shrinks by one. */
+int nk_index_remove_swap(NkIndex *ix, uint64_t row);
+/* Fill the index with n_rows synthetic rows generated ON DEVICE by the counter-based generator shared
+ * with the oracle (oracle/knn_oracle.c orc_fill_uniform): U[-1,1), element (r,j) depends only on
+ * (seed, r, j).  Used by bench.py and the large-shape tests so 40 GB corpora never cross PCIe. */
+int nk_index_fill_uniform(NkIndex *ix, uint64_t n_rows, uint64_t seed);
+/* Single-device index only: this process owns rows [row_base, row_base+n) of a larger corpus
+ * (multi-process sharding, one rank per GPU).  Emitted indices are global.  Also offsets the synthetic
+ * generator so rank g's rows equal rows row_base.. of the global stream. */
+int nk_index_set_row_base(NkIndex *ix, uint64_t row_base);
+/* Adopt caller-owned device memory as the (single) shard; not freed by nk_index_release. */
+int nk_index_attach_device_rows(NkIndex *ix, void *rows_dev, uint64_t n_rows);
+int nk_index_set_path(NkIndex *ix, int path);
+uint64_t nk_index_rows(const NkIndex *ix);
+int nk_index_stats(const NkIndex *ix, NkStats *out);
+/* Device-side timing of the scan kernels (bench.py roofline): when enabled, every scan launch is
+ * bracketed by CUDA events on its stream.  nk_index_scan_time_ms synchronises, returns the summed
+ * duration and launch count since the last call, and resets the counters. */
+int nk_index_enable_timing(NkIndex *ix, int enabled);
+int nk_index_scan_time_ms(NkIndex *ix, double *total_ms, uint64_t *scan_launches);
+/* Copy n_rows rows starting at global row `row` back to the host (tests / Serialize). */
+int nk_index_read_rows(NkIndex *ix, uint64_t row, uint64_t n_rows, void *rows_host);
+
+/* Batched fused search.  queries_host: [Q x dim] fp32.  out_idx/out_score: caller-owned [Q x k]
+ * (row stride k).  Returns the number of results per query, min(k, N) (cuda_bridge.go:647-649;
+ * 0 for k == 0 or an empty index, cuda_bridge.go:644-646, gpu.go:1540-1542), or -1 on error.
+ * Order: cosine/dot — score descending, ties by row index ascending; euclidean — distance ascending,
+ * ties by row index ascending, out_score = the distance (callers apply 1/(1+d), similarity.go:152-158).
+ * Synchronous: inputs are consumed and outputs complete on return. */
+int nk_search(NkIndex *ix, const float *queries_host, uint32_t Q, uint32_t k, uint32_t *out_idx, float *out_score);
+
+/* Same, single-device index, everything device-resident and asynchronous on `stream` (a cudaStream_t,
+ * NULL = the index's own stream).  queries_dev [Q x dim] fp32; out_idx_dev/out_score_dev [Q x k]. */
+int nk_search_device(NkIndex *ix, const float *queries_dev, uint32_t Q, uint32_t k, uint32_t *out_idx_dev,
+                     float *out_score_dev, void *stream);
+
+/* Multi-process sharding (one rank per GPU): emit this shard's sorted candidate list as packed 64-bit
+ * keys [Q x k] (order-preserving score bits << 32 | ~row index; larger key = better), to be exchanged
+ * (e.g. ncclAllGather of Q*k*8 bytes per rank) and merged with nk_merge_keys_device. */
+int nk_search_keys_device(NkIndex *ix, const float *queries_dev, uint32_t Q, uint32_t k, uint64_t *out_keys_dev,
+                          void *stream);
+/* Merge n_lists candidate lists laid out [n_lists][Q][k] into final [Q x k] idx/score on the current
+ * device of `device_id`.  metric selects the score decoding (euclidean: distance). */
+int nk_merge_keys_device(int device_id, const uint64_t *keys_dev, uint32_t n_lists, uint32_t Q, uint32_t k,
+                         int metric, uint32_t *out_idx_dev, float *out_score_dev, void *stream);
+
+/* Score an explicit subset of rows (global indices) against one query and return them sorted
+ * (EmbeddingIndex.ScoreSubset gpu.go:1552-1616, ClusterIndex.SearchCandidates kmeans.go:839-895).
+ * out arrays have length min(k, n_rows_subset) per query; returns that length or -1. */
+int nk_score_subset(NkIndex *ix, const float *query_host, const uint32_t *rows_host, uint32_t n_subset, uint32_t k,
+                    uint32_t *out_idx, float *out_score);
+
+/* Synthetic fp32 query block from the shared generator, on the device of a single-device index. */
+int nk_fill_uniform_device(int device_id, float *out_dev, uint64_t n_rows, uint32_t dim, uint64_t seed,
+                           uint64_t row_base, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NORNIC_KNN_H */

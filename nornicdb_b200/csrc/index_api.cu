@@ -1,0 +1,597 @@
+// index_api.cu — the fused batched kNN API (Part 2 of include/nornic_knn.h).
+//
+// NkIndex is the device-side half of gpu.EmbeddingIndex (pkg/gpu/gpu.go:1224-1260): a flat row-major
+// [N x dim] corpus resident in HBM, row-sharded by contiguous ranges over the GPUs of this process.
+// nk_search replaces cuda.Device.Search (pkg/gpu/cuda/cuda_bridge.go:643-686: NewBuffer + NewEmptyBuffer
+// + CosineSimilarity + TopK, with a cudaMalloc/cudaFree pair and an n-float D2H per query) by one
+// fused scan per shard + a candidate merge; nothing is allocated per query and only Q*k results leave
+// the device.
+#include <algorithm>
+#include <mutex>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace nk {
+int scan_tensor(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *out_keys, uint64_t *launches);
+bool scan_tensor_supported(const DeviceInfo &di, const ScanArgs &a);
+}
+
+struct NkShard {
+    int device = 0;
+    nk::DeviceInfo di;
+    cudaStream_t stream = nullptr;
+    void *rows = nullptr;
+    bool owns = true;
+    uint64_t n = 0, cap = 0, base = 0;
+    nk::Workspace ws;
+    uint64_t *h_keys = nullptr;  // pinned staging for multi-shard host merge
+    size_t h_keys_bytes = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // pending scan-kernel event pairs
+    std::vector<uint64_t> timing_launches;
+};
+
+struct NkIndex {
+    uint32_t dim = 0;
+    int dtype = NK_DTYPE_F32;
+    int metric = NK_METRIC_COSINE;
+    int path = NK_PATH_AUTO;
+    bool timing_on = false;
+    uint64_t row_base = 0;
+    std::vector<NkShard> shards;
+    NkStats stats{};
+    std::mutex mu;
+    size_t esz() const { return dtype == NK_DTYPE_F16 ? 2 : 4; }
+    uint64_t rows() const {
+        uint64_t t = 0;
+        for (auto &s : shards) t += s.n;
+        return t;
+    }
+};
+
+static int shard_reserve_rows(NkIndex *ix, NkShard &s, uint64_t need_rows, bool keep) {
+    if (need_rows <= s.cap && s.rows) return 0;
+    if (!s.owns) {
+        nk::set_error("cannot grow attached (caller-owned) device rows");
+        return -1;
+    }
+    uint64_t cap = keep ? std::max<uint64_t>(need_rows, s.cap + s.cap / 2) : need_rows;
+    if (cap < 16) cap = 16;
+    void *p = nullptr;
+    size_t rb = (size_t)ix->dim * ix->esz();
+    NK_CUDA_OK(cudaMalloc(&p, cap * rb));
+    if (s.rows) {
+        if (keep && s.n) NK_CUDA_OK(cudaMemcpyAsync(p, s.rows, s.n * rb, cudaMemcpyDeviceToDevice, s.stream));
+        NK_CUDA_OK(cudaStreamSynchronize(s.stream));
+        NK_CUDA_OK(cudaFree(s.rows));
+    }
+    s.rows = p;
+    s.cap = cap;
+    return 0;
+}
+
+static void rebase(NkIndex *ix) {
+    uint64_t b = ix->row_base;
+    for (auto &s : ix->shards) {
+        s.base = b;
+        b += s.n;
+    }
+    ix->stats.rows = ix->rows();
+}
+
+// Locate the shard holding global row `row` (relative to row_base).
+static NkShard *find_shard(NkIndex *ix, uint64_t row, uint64_t *local) {
+    for (auto &s : ix->shards)
+        if (row >= s.base - ix->row_base && row < s.base - ix->row_base + s.n) {
+            *local = row - (s.base - ix->row_base);
+            return &s;
+        }
+    return nullptr;
+}
+
+static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uint32_t k, uint64_t *out_keys,
+                    cudaStream_t stream) {
+    nk::ScanArgs a;
+    a.rows = s.rows; a.dtype = ix->dtype; a.n = (uint32_t)s.n; a.dim = ix->dim; a.row_base = s.base;
+    a.queries = q_dev; a.Q = Q; a.k = k; a.metric = ix->metric; a.stream = stream;
+    bool tensor_ok = nk::scan_tensor_supported(s.di, a);
+    bool use_tensor = false;
+    if (ix->path == NK_PATH_TENSOR) {
+        if (!tensor_ok) {
+            nk::set_error("tensor path does not support this shape (dim=%u dtype=%d Q=%u k=%u)", ix->dim, ix->dtype, Q, k);
+            return -1;
+        }
+        use_tensor = true;
+    } else if (ix->path == NK_PATH_AUTO) {
+        // Below ~16 queries the CUDA-core scan is already HBM-bound (2*Q flop/byte*... see DESIGN.md).
+        use_tensor = tensor_ok && Q > 16;
+    }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const uint64_t l0 = ix->stats.kernel_launches;
+    if (ix->timing_on) {
+        NK_CUDA_OK(cudaEventCreate(&e0));
+        NK_CUDA_OK(cudaEventCreate(&e1));
+        NK_CUDA_OK(cudaEventRecord(e0, stream));
+    }
+    int rc = use_tensor ? nk::scan_tensor(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches)
+                        : nk::scan_simt(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches);
+    if (ix->timing_on) {
+        NK_CUDA_OK(cudaEventRecord(e1, stream));
+        s.timing.emplace_back(e0, e1);
+        s.timing_launches.push_back(ix->stats.kernel_launches - l0);
+    }
+    if (rc == 0) ix->stats.bytes_scanned += (uint64_t)s.n * ix->dim * ix->esz() * (use_tensor ? 1 : ((Q + 7) / 8));
+    return rc;
+}
+
+extern "C" {
+
+const char *nk_last_error(void) { return nk::get_error(); }
+const char *nk_version(void) { return "nornic-knn-b200 0.1 (sm_100a)"; }
+
+NkIndex *nk_index_create(const int *device_ids, int n_devices, uint32_t dim, int dtype, int metric) {
+    if (n_devices <= 0 || !device_ids || dim == 0) {
+        nk::set_error("nk_index_create: need >= 1 device and dim > 0");
+        return nullptr;
+    }
+    if (dtype != NK_DTYPE_F32 && dtype != NK_DTYPE_F16) {
+        nk::set_error("nk_index_create: unknown dtype %d", dtype);
+        return nullptr;
+    }
+    if (metric < NK_METRIC_COSINE || metric > NK_METRIC_EUCLIDEAN) {
+        nk::set_error("nk_index_create: unknown metric %d", metric);
+        return nullptr;
+    }
+    NkIndex *ix = new NkIndex();
+    ix->dim = dim; ix->dtype = dtype; ix->metric = metric;
+    ix->stats.dim = dim; ix->stats.n_devices = (uint32_t)n_devices;
+    ix->shards.resize(n_devices);
+    for (int i = 0; i < n_devices; ++i) {
+        NkShard &s = ix->shards[i];
+        s.device = device_ids[i];
+        cudaError_t e = cudaSetDevice(s.device);
+        if (e == cudaSuccess && nk::query_device_info(s.device, &s.di) != 0) e = cudaErrorUnknown;
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&s.ws.flags, sizeof(int) * 4);
+        if (e == cudaSuccess) e = cudaMemset(s.ws.flags, 0, sizeof(int) * 4);
+        if (e != cudaSuccess) {
+            if (e != cudaErrorUnknown) nk::set_error("nk_index_create(device %d): %s", s.device, cudaGetErrorString(e));
+            cudaGetLastError();
+            nk_index_release(ix);
+            return nullptr;
+        }
+    }
+    return ix;
+}
+
+void nk_index_release(NkIndex *ix) {
+    if (!ix) return;
+    for (auto &s : ix->shards) {
+        cudaSetDevice(s.device);
+        if (s.stream) {
+            cudaStreamSynchronize(s.stream);
+            cudaStreamDestroy(s.stream);
+        }
+        if (s.rows && s.owns) cudaFree(s.rows);
+        if (s.h_keys) cudaFreeHost(s.h_keys);
+        s.ws.release();
+    }
+    delete ix;
+}
+
+int nk_index_upload(NkIndex *ix, const void *rows_host, uint64_t n_rows) {
+    if (!ix) { nk::set_error("null index"); return -1; }
+    if (n_rows && !rows_host) { nk::set_error("null rows"); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    const size_t rb = (size_t)ix->dim * ix->esz();
+    const uint64_t G = ix->shards.size();
+    if (n_rows / G + 1 > 0xfffffff0ull) { nk::set_error("shard exceeds 2^32 rows"); return -1; }
+    uint64_t off = 0;
+    for (uint64_t g = 0; g < G; ++g) {
+        NkShard &s = ix->shards[g];
+        uint64_t cnt = n_rows * (g + 1) / G - n_rows * g / G;  // contiguous range [g*N/G, (g+1)*N/G)
+        NK_CUDA_OK(cudaSetDevice(s.device));
+        if (!s.owns) { s.rows = nullptr; s.owns = true; s.cap = 0; }
+        s.n = 0;
+        if (shard_reserve_rows(ix, s, cnt, false)) return -1;
+        if (cnt) NK_CUDA_OK(cudaMemcpyAsync(s.rows, (const char *)rows_host + off * rb, cnt * rb, cudaMemcpyHostToDevice, s.stream));
+        s.n = cnt;
+        off += cnt;
+        ix->stats.bytes_h2d += cnt * rb;
+    }
+    for (auto &s : ix->shards) {
+        NK_CUDA_OK(cudaSetDevice(s.device));
+        NK_CUDA_OK(cudaStreamSynchronize(s.stream));
+    }
+    rebase(ix);
+    return 0;
+}
+
+int nk_index_append(NkIndex *ix, const void *rows_host, uint64_t n_rows) {
+    if (!ix) { nk::set_error("null index"); return -1; }
+    if (n_rows == 0) return 0;
+    if (!rows_host) { nk::set_error("null rows"); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    NkShard &s = ix->shards.back();
+    const size_t rb = (size_t)ix->dim * ix->esz();
+    if (s.n + n_rows > 0xfffffff0ull) { nk::set_error("shard exceeds 2^32 rows"); return -1; }
+    NK_CUDA_OK(cudaSetDevice(s.device));
+    if (shard_reserve_rows(ix, s, s.n + n_rows, true)) return -1;
+    NK_CUDA_OK(cudaMemcpyAsync((char *)s.rows + s.n * rb, rows_host, n_rows * rb, cudaMemcpyHostToDevice, s.stream));
+    NK_CUDA_OK(cudaStreamSynchronize(s.stream));
+    s.n += n_rows;
+    ix->stats.bytes_h2d += n_rows * rb;
+    rebase(ix);
+    return 0;
+}
+
+int nk_index_update_row(NkIndex *ix, uint64_t row, const void *row_host) {
+    if (!ix || !row_host) { nk::set_error("null argument"); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    uint64_t local;
+    NkShard *s = find_shard(ix, row, &local);
+    if (!s) { nk::set_error("row %llu out of range", (unsigned long long)row); return -1; }
+    const size_t rb = (size_t)ix->dim * ix->esz();
+    NK_CUDA_OK(cudaSetDevice(s->device));
+    NK_CUDA_OK(cudaMemcpyAsync((char *)s->rows + local * rb, row_host, rb, cudaMemcpyHostToDevice, s->stream));
+    NK_CUDA_OK(cudaStreamSynchronize(s->stream));
+    ix->stats.bytes_h2d += rb;
+    return 0;
+}
+
+int nk_index_remove_swap(NkIndex *ix, uint64_t row) {
+    if (!ix) { nk::set_error("null index"); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    uint64_t total = ix->rows();
+    if (row >= total) { nk::set_error("row %llu out of range", (unsigned long long)row); return -1; }
+    // last non-empty shard holds the last row
+    NkShard *last = nullptr;
+    for (auto it = ix->shards.rbegin(); it != ix->shards.rend(); ++it)
+        if (it->n) { last = &*it; break; }
+    uint64_t local;
+    NkShard *s = find_shard(ix, row, &local);
+    const size_t rb = (size_t)ix->dim * ix->esz();
+    if (row != total - 1) {
+        const char *src = (const char *)last->rows + (last->n - 1) * rb;
+        char *dst = (char *)s->rows + local * rb;
+        NK_CUDA_OK(cudaSetDevice(s->device));
+        NK_CUDA_OK(cudaMemcpy(dst, src, rb, cudaMemcpyDefault));  // same or peer device
+    }
+    last->n -= 1;
+    rebase(ix);
+    return 0;
+}
+
+int nk_index_fill_uniform(NkIndex *ix, uint64_t n_rows, uint64_t seed) {
+    if (!ix) { nk::set_error("null index"); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    const uint64_t G = ix->shards.size();
+    if (n_rows / G + 1 > 0xfffffff0ull) { nk::set_error("shard exceeds 2^32 rows"); return -1; }
+    uint64_t off = 0;
+    for (uint64_t g = 0; g < G; ++g) {
+        NkShard &s = ix->shards[g];
+        uint64_t cnt = n_rows * (g + 1) / G - n_rows * g / G;
+        NK_CUDA_OK(cudaSetDevice(s.device));
+        if (!s.owns) { s.rows = nullptr; s.owns = true; s.cap = 0; }
+        s.n = 0;
+        if (shard_reserve_rows(ix, s, cnt, false)) return -1;
+        if (nk::fill_uniform(s.rows, ix->dtype, cnt, ix->dim, seed, ix->row_base + off, s.stream)) return -1;
+        ix->stats.kernel_launches++;
+        s.n = cnt;
+        off += cnt;
+    }
+    for (auto &s : ix->shards) {
+        NK_CUDA_OK(cudaSetDevice(s.device));
+        NK_CUDA_OK(cudaStreamSynchronize(s.stream));
+    }
+    rebase(ix);
+    return 0;
+}
+
+int nk_index_set_row_base(NkIndex *ix, uint64_t row_base) {
+    if (!ix) { nk::set_error("null index"); return -1; }
+    if (ix->shards.size() != 1) { nk::set_error("row_base applies to single-device indexes"); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->row_base = row_base;
+    rebase(ix);
+    return 0;
+}
+
+int nk_index_attach_device_rows(NkIndex *ix, void *rows_dev, uint64_t n_rows) {
+    if (!ix) { nk::set_error("null index"); return -1; }
+    if (ix->shards.size() != 1) { nk::set_error("attach applies to single-device indexes"); return -1; }
+    if (n_rows > 0xfffffff0ull) { nk::set_error("shard exceeds 2^32 rows"); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    NkShard &s = ix->shards[0];
+    NK_CUDA_OK(cudaSetDevice(s.device));
+    if (s.rows && s.owns) NK_CUDA_OK(cudaFree(s.rows));
+    s.rows = rows_dev; s.owns = false; s.n = n_rows; s.cap = n_rows;
+    rebase(ix);
+    return 0;
+}
+
+int nk_index_set_path(NkIndex *ix, int path) {
+    if (!ix || path < NK_PATH_AUTO || path > NK_PATH_TENSOR) { nk::set_error("bad path"); return -1; }
+    ix->path = path;
+    return 0;
+}
+
+uint64_t nk_index_rows(const NkIndex *ix) { return ix ? ix->rows() : 0; }
+
+int nk_index_stats(const NkIndex *ix, NkStats *out) {
+    if (!ix || !out) { nk::set_error("null argument"); return -1; }
+    *out = ix->stats;
+    out->rows = ix->rows();
+    return 0;
+}
+
+int nk_index_enable_timing(NkIndex *ix, int enabled) {
+    if (!ix) { nk::set_error("null index"); return -1; }
+    ix->timing_on = enabled != 0;
+    return 0;
+}
+
+int nk_index_scan_time_ms(NkIndex *ix, double *total_ms, uint64_t *scan_launches) {
+    if (!ix || !total_ms || !scan_launches) { nk::set_error("null argument"); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    double ms = 0.0;
+    uint64_t n = 0;
+    for (auto &s : ix->shards) {
+        NK_CUDA_OK(cudaSetDevice(s.device));
+        for (size_t i = 0; i < s.timing.size(); ++i) {
+            float t = 0.0f;
+            NK_CUDA_OK(cudaEventSynchronize(s.timing[i].second));
+            NK_CUDA_OK(cudaEventElapsedTime(&t, s.timing[i].first, s.timing[i].second));
+            ms += t;
+            n += s.timing_launches[i];
+            cudaEventDestroy(s.timing[i].first);
+            cudaEventDestroy(s.timing[i].second);
+        }
+        s.timing.clear();
+        s.timing_launches.clear();
+    }
+    *total_ms = ms;
+    *scan_launches = n;
+    return 0;
+}
+
+int nk_index_read_rows(NkIndex *ix, uint64_t row, uint64_t n_rows, void *rows_host) {
+    if (!ix || (!rows_host && n_rows)) { nk::set_error("null argument"); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    const size_t rb = (size_t)ix->dim * ix->esz();
+    for (uint64_t i = 0; i < n_rows;) {
+        uint64_t local;
+        NkShard *s = find_shard(ix, row + i, &local);
+        if (!s) { nk::set_error("row %llu out of range", (unsigned long long)(row + i)); return -1; }
+        uint64_t cnt = std::min<uint64_t>(n_rows - i, s->n - local);
+        NK_CUDA_OK(cudaSetDevice(s->device));
+        NK_CUDA_OK(cudaMemcpy((char *)rows_host + i * rb, (const char *)s->rows + local * rb, cnt * rb, cudaMemcpyDeviceToHost));
+        ix->stats.bytes_d2h += cnt * rb;
+        i += cnt;
+    }
+    return 0;
+}
+
+static int check_flags(NkShard &s) {
+    int h[1] = {0};
+    NK_CUDA_OK(cudaMemcpyAsync(h, s.ws.flags, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    NK_CUDA_OK(cudaStreamSynchronize(s.stream));
+    if (h[0]) {
+        cudaMemsetAsync(s.ws.flags, 0, sizeof(int), s.stream);
+        nk::set_error("internal: candidate buffer overflow (flag=%d)", h[0]);
+        return -1;
+    }
+    return 0;
+}
+
+int nk_search(NkIndex *ix, const float *queries_host, uint32_t Q, uint32_t k, uint32_t *out_idx, float *out_score) {
+    if (!ix) { nk::set_error("null index"); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    const uint64_t N = ix->rows();
+    if (k == 0 || N == 0 || Q == 0) return 0;  // cuda_bridge.go:644-646, gpu.go:1540-1542
+    if (!queries_host || !out_idx || !out_score) { nk::set_error("null argument"); return -1; }
+    const uint32_t ke = k > N ? (uint32_t)N : k;  // cuda_bridge.go:647-649
+    if (ke > NK_MAX_K) { nk::set_error("k=%u exceeds NK_MAX_K=%u", ke, NK_MAX_K); return -1; }
+    const size_t qbytes = (size_t)Q * ix->dim * sizeof(float);
+    ix->stats.searches++;
+    ix->stats.queries += Q;
+
+    std::vector<NkShard *> live;
+    for (auto &s : ix->shards)
+        if (s.n) live.push_back(&s);
+
+    // Launch every shard asynchronously, then collect.
+    for (NkShard *s : live) {
+        NK_CUDA_OK(cudaSetDevice(s->device));
+        if (nk::ws_reserve((void **)&s->ws.queries, &s->ws.queries_bytes, qbytes)) return -1;
+        if (nk::ws_reserve((void **)&s->ws.keys, &s->ws.keys_bytes, (size_t)Q * ke * 8)) return -1;
+        NK_CUDA_OK(cudaMemcpyAsync(s->ws.queries, queries_host, qbytes, cudaMemcpyHostToDevice, s->stream));
+        ix->stats.bytes_h2d += qbytes;
+        if (run_scan(ix, *s, s->ws.queries, Q, ke, s->ws.keys, s->stream)) return -1;
+    }
+
+    if (live.size() == 1) {
+        NkShard *s = live[0];
+        NK_CUDA_OK(cudaSetDevice(s->device));
+        if (nk::ws_reserve((void **)&s->ws.out_idx, &s->ws.out_idx_bytes, (size_t)Q * ke * 4)) return -1;
+        if (nk::ws_reserve((void **)&s->ws.out_score, &s->ws.out_score_bytes, (size_t)Q * ke * 4)) return -1;
+        if (nk::decode_keys(s->ws.keys, Q, ke, ix->metric, s->ws.out_idx, s->ws.out_score, s->stream)) return -1;
+        ix->stats.kernel_launches++;
+        NK_CUDA_OK(cudaMemcpy2DAsync(out_idx, (size_t)k * 4, s->ws.out_idx, (size_t)ke * 4, (size_t)ke * 4, Q,
+                                     cudaMemcpyDeviceToHost, s->stream));
+        NK_CUDA_OK(cudaMemcpy2DAsync(out_score, (size_t)k * 4, s->ws.out_score, (size_t)ke * 4, (size_t)ke * 4, Q,
+                                     cudaMemcpyDeviceToHost, s->stream));
+        ix->stats.bytes_d2h += (uint64_t)Q * ke * 8;
+        if (check_flags(*s)) return -1;
+        return (int)ke;
+    }
+
+    // Multi-shard: gather the per-GPU candidate lists (Q*k*8 B each) and merge on the host with the
+    // same (score desc, row asc) order (SURVEY.md §8e "small Q: async D2H + host k-way merge").
+    const size_t kbytes = (size_t)Q * ke * 8;
+    for (NkShard *s : live) {
+        NK_CUDA_OK(cudaSetDevice(s->device));
+        if (s->h_keys_bytes < kbytes) {
+            if (s->h_keys) cudaFreeHost(s->h_keys);
+            s->h_keys = nullptr; s->h_keys_bytes = 0;
+            NK_CUDA_OK(cudaMallocHost((void **)&s->h_keys, kbytes + kbytes / 4));
+            s->h_keys_bytes = kbytes + kbytes / 4;
+        }
+        NK_CUDA_OK(cudaMemcpyAsync(s->h_keys, s->ws.keys, kbytes, cudaMemcpyDeviceToHost, s->stream));
+        ix->stats.bytes_d2h += kbytes;
+    }
+    for (NkShard *s : live) {
+        NK_CUDA_OK(cudaSetDevice(s->device));
+        if (check_flags(*s)) return -1;
+    }
+    std::vector<uint64_t> tmp(live.size() * (size_t)ke);
+    for (uint32_t q = 0; q < Q; ++q) {
+        size_t m = 0;
+        for (NkShard *s : live)
+            for (uint32_t i = 0; i < ke; ++i) {
+                uint64_t key = s->h_keys[(size_t)q * ke + i];
+                if (key) tmp[m++] = key;
+            }
+        size_t take = std::min<size_t>(ke, m);
+        std::partial_sort(tmp.begin(), tmp.begin() + take, tmp.begin() + m, std::greater<uint64_t>());
+        for (uint32_t i = 0; i < ke; ++i) {
+            if (i < take) {
+                float sc = nk::key_score(tmp[i]);
+                if (ix->metric == NK_METRIC_EUCLIDEAN) sc = sqrtf(std::max(-sc, 0.0f));
+                out_idx[(size_t)q * k + i] = nk::key_row(tmp[i]);
+                out_score[(size_t)q * k + i] = sc;
+            } else {
+                out_idx[(size_t)q * k + i] = 0xffffffffu;
+                out_score[(size_t)q * k + i] = 0.0f;
+            }
+        }
+    }
+    return (int)ke;
+}
+
+static int single_shard(NkIndex *ix, NkShard **out) {
+    if (!ix) { nk::set_error("null index"); return -1; }
+    if (ix->shards.size() != 1) { nk::set_error("device-resident search needs a single-device index"); return -1; }
+    *out = &ix->shards[0];
+    return 0;
+}
+
+int nk_search_keys_device(NkIndex *ix, const float *queries_dev, uint32_t Q, uint32_t k, uint64_t *out_keys_dev,
+                          void *stream) {
+    NkShard *s;
+    if (single_shard(ix, &s)) return -1;
+    if (k == 0 || Q == 0) return 0;
+    if (!queries_dev || !out_keys_dev) { nk::set_error("null argument"); return -1; }
+    if (k > NK_MAX_K) { nk::set_error("k=%u exceeds NK_MAX_K=%u", k, NK_MAX_K); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    NK_CUDA_OK(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    ix->stats.searches++;
+    ix->stats.queries += Q;
+    if (s->n == 0) {
+        NK_CUDA_OK(cudaMemsetAsync(out_keys_dev, 0, (size_t)Q * k * 8, st));
+        return (int)k;
+    }
+    if (run_scan(ix, *s, queries_dev, Q, k, out_keys_dev, st)) return -1;
+    return (int)k;
+}
+
+int nk_search_device(NkIndex *ix, const float *queries_dev, uint32_t Q, uint32_t k, uint32_t *out_idx_dev,
+                     float *out_score_dev, void *stream) {
+    NkShard *s;
+    if (single_shard(ix, &s)) return -1;
+    const uint64_t N = s->n;
+    if (k == 0 || N == 0 || Q == 0) return 0;
+    if (!queries_dev || !out_idx_dev || !out_score_dev) { nk::set_error("null argument"); return -1; }
+    if (k > N) { nk::set_error("nk_search_device: k=%u > rows=%llu (clamp on the host side)", k, (unsigned long long)N); return -1; }
+    if (k > NK_MAX_K) { nk::set_error("k=%u exceeds NK_MAX_K=%u", k, NK_MAX_K); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    NK_CUDA_OK(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    if (nk::ws_reserve((void **)&s->ws.keys, &s->ws.keys_bytes, (size_t)Q * k * 8)) return -1;
+    ix->stats.searches++;
+    ix->stats.queries += Q;
+    if (run_scan(ix, *s, queries_dev, Q, k, s->ws.keys, st)) return -1;
+    if (nk::decode_keys(s->ws.keys, Q, k, ix->metric, out_idx_dev, out_score_dev, st)) return -1;
+    ix->stats.kernel_launches++;
+    return (int)k;
+}
+
+int nk_merge_keys_device(int device_id, const uint64_t *keys_dev, uint32_t n_lists, uint32_t Q, uint32_t k, int metric,
+                         uint32_t *out_idx_dev, float *out_score_dev, void *stream) {
+    if (k == 0 || Q == 0 || n_lists == 0) return 0;
+    if (!keys_dev || !out_idx_dev || !out_score_dev) { nk::set_error("null argument"); return -1; }
+    NK_CUDA_OK(cudaSetDevice(device_id));
+    cudaStream_t st = (cudaStream_t)stream;
+    uint64_t *merged = nullptr;
+    NK_CUDA_OK(cudaMallocAsync((void **)&merged, (size_t)Q * k * 8, st));
+    int rc = nk::merge_keys(keys_dev, n_lists, (size_t)Q * k, k, Q, k, merged, st);
+    if (rc == 0) rc = nk::decode_keys(merged, Q, k, metric, out_idx_dev, out_score_dev, st);
+    cudaFreeAsync(merged, st);
+    return rc;
+}
+
+int nk_score_subset(NkIndex *ix, const float *query_host, const uint32_t *rows_host, uint32_t n_subset, uint32_t k,
+                    uint32_t *out_idx, float *out_score) {
+    NkShard *s;
+    if (single_shard(ix, &s)) return -1;
+    if (n_subset == 0 || k == 0) return 0;
+    if (!query_host || !rows_host || !out_idx || !out_score) { nk::set_error("null argument"); return -1; }
+    const uint32_t ke = std::min(k, n_subset);
+    if (ke > NK_MAX_K) { nk::set_error("k=%u exceeds NK_MAX_K=%u", ke, NK_MAX_K); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    for (uint32_t i = 0; i < n_subset; ++i)
+        if (rows_host[i] < ix->row_base || rows_host[i] - ix->row_base >= s->n) {
+            nk::set_error("subset row %u out of range", rows_host[i]);
+            return -1;
+        }
+    NK_CUDA_OK(cudaSetDevice(s->device));
+    const size_t rb = (size_t)ix->dim * ix->esz();
+    uint32_t *d_rows = nullptr;
+    void *d_gather = nullptr;
+    NK_CUDA_OK(cudaMallocAsync((void **)&d_rows, (size_t)n_subset * 4, s->stream));
+    NK_CUDA_OK(cudaMallocAsync(&d_gather, (size_t)n_subset * rb, s->stream));
+    std::vector<uint32_t> local(rows_host, rows_host + n_subset);
+    for (auto &r : local) r -= (uint32_t)ix->row_base;
+    int rc = 0;
+    std::vector<uint32_t> pos((size_t)ke);
+    do {
+        if (cudaMemcpyAsync(d_rows, local.data(), (size_t)n_subset * 4, cudaMemcpyHostToDevice, s->stream) != cudaSuccess) { rc = -1; break; }
+        if (nk::gather_rows(s->rows, ix->dtype, ix->dim, d_rows, n_subset, d_gather, s->stream)) { rc = -1; break; }
+        if (nk::ws_reserve((void **)&s->ws.queries, &s->ws.queries_bytes, (size_t)ix->dim * 4)) { rc = -1; break; }
+        if (nk::ws_reserve((void **)&s->ws.keys, &s->ws.keys_bytes, (size_t)ke * 8)) { rc = -1; break; }
+        if (nk::ws_reserve((void **)&s->ws.out_idx, &s->ws.out_idx_bytes, (size_t)ke * 4)) { rc = -1; break; }
+        if (nk::ws_reserve((void **)&s->ws.out_score, &s->ws.out_score_bytes, (size_t)ke * 4)) { rc = -1; break; }
+        if (cudaMemcpyAsync(s->ws.queries, query_host, (size_t)ix->dim * 4, cudaMemcpyHostToDevice, s->stream) != cudaSuccess) { rc = -1; break; }
+        nk::ScanArgs a;
+        a.rows = d_gather; a.dtype = ix->dtype; a.n = n_subset; a.dim = ix->dim; a.row_base = 0;
+        a.queries = s->ws.queries; a.Q = 1; a.k = ke; a.metric = ix->metric; a.stream = s->stream;
+        if (nk::scan_simt(s->di, a, s->ws, s->ws.keys, &ix->stats.kernel_launches)) { rc = -1; break; }
+        if (nk::decode_keys(s->ws.keys, 1, ke, ix->metric, s->ws.out_idx, s->ws.out_score, s->stream)) { rc = -1; break; }
+        if (cudaMemcpyAsync(pos.data(), s->ws.out_idx, (size_t)ke * 4, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) { rc = -1; break; }
+        if (cudaMemcpyAsync(out_score, s->ws.out_score, (size_t)ke * 4, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) { rc = -1; break; }
+    } while (0);
+    cudaFreeAsync(d_rows, s->stream);
+    cudaFreeAsync(d_gather, s->stream);
+    if (rc != 0) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) nk::set_error("nk_score_subset: %s", cudaGetErrorString(e));
+        cudaStreamSynchronize(s->stream);
+        return -1;
+    }
+    if (check_flags(*s)) return -1;
+    // positions within the subset -> global row ids (ties broken by subset position, like the stable
+    // order of ScoreSubset's input list)
+    for (uint32_t i = 0; i < ke; ++i) out_idx[i] = pos[i] < n_subset ? rows_host[pos[i]] : 0xffffffffu;
+    return (int)ke;
+}
+
+int nk_fill_uniform_device(int device_id, float *out_dev, uint64_t n_rows, uint32_t dim, uint64_t seed,
+                           uint64_t row_base, void *stream) {
+    NK_CUDA_OK(cudaSetDevice(device_id));
+    return nk::fill_uniform(out_dev, NK_DTYPE_F32, n_rows, dim, seed, row_base, (cudaStream_t)stream);
+}
+
+}  // extern "C"

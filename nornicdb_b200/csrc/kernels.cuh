@@ -1,0 +1,67 @@
+// kernels.cuh — internal launcher interface between the C-ABI host code and the kernels.
+#pragma once
+#include "common.cuh"
+
+namespace nk {
+
+struct DeviceInfo {
+    int device_id = 0;
+    int num_sms = 148;
+    size_t max_smem_optin = 0;
+    int cc = 0;
+};
+int query_device_info(int device_id, DeviceInfo *out);
+
+// Grow-only device scratch of one shard (never freed between searches: no per-query cudaMalloc,
+// unlike cuda.Device.Search, cuda_bridge.go:652-663).
+struct Workspace {
+    uint64_t *cand = nullptr;     size_t cand_bytes = 0;     // [grid][QT][cap] candidate buffers
+    uint64_t *partial = nullptr;  size_t partial_bytes = 0;  // [Q][grid][k] per-CTA sorted lists
+    uint64_t *keys = nullptr;     size_t keys_bytes = 0;     // [Q][k] merged keys
+    float *queries = nullptr;     size_t queries_bytes = 0;  // staged queries (host API)
+    uint32_t *out_idx = nullptr;  size_t out_idx_bytes = 0;
+    float *out_score = nullptr;   size_t out_score_bytes = 0;
+    float *qaux = nullptr;        size_t qaux_bytes = 0;     // tensor path: split / normalised queries
+    float *rownorm = nullptr;     size_t rownorm_bytes = 0;  // tensor path: per-row inverse norms / sq norms
+    int *flags = nullptr;                                    // [0] = candidate-buffer overflow (must stay 0)
+    int release();
+};
+int ws_reserve(void **p, size_t *cur, size_t need);
+
+struct ScanArgs {
+    const void *rows = nullptr;  // [n x dim] row-major, fp32 or fp16
+    int dtype = NK_DTYPE_F32;
+    uint32_t n = 0;
+    uint32_t dim = 0;
+    uint64_t row_base = 0;       // global index of row 0
+    const float *queries = nullptr;  // device [Q x dim] fp32
+    uint32_t Q = 0;
+    uint32_t k = 0;              // 1..NK_MAX_K (may exceed n: missing slots are key 0)
+    int metric = NK_METRIC_COSINE;
+    cudaStream_t stream = nullptr;
+};
+
+// Fused distance + top-k scan on CUDA cores (small Q, any dim / dtype / alignment).
+// Writes per-query sorted candidate keys [Q][k] to out_keys (device).
+int scan_simt(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *out_keys, uint64_t *launches);
+
+// Merge n_lists sorted (or unsorted) key lists per query into the best k, sorted descending.
+// key(list l, query q, slot i) = keys[l*list_stride + q*q_stride + i].
+int merge_keys(const uint64_t *keys, uint32_t n_lists, size_t list_stride, size_t q_stride, uint32_t Q, uint32_t k,
+               uint64_t *out_keys, cudaStream_t stream);
+// keys [Q][k] -> idx/score [Q][k]; euclidean decodes score = sqrt(-s).
+int decode_keys(const uint64_t *keys, uint32_t Q, uint32_t k, int metric, uint32_t *out_idx, float *out_score,
+                cudaStream_t stream);
+
+// Row utilities (legacy ABI + index maintenance).
+int row_norms(const float *rows, float *norms, uint32_t n, uint32_t dim, cudaStream_t s);
+int normalize_rows(float *rows, uint32_t n, uint32_t dim, cudaStream_t s);
+int row_scores(const float *rows, const float *query, float *scores, uint32_t n, uint32_t dim, int normalized,
+               cudaStream_t s);
+int topk_scores(const DeviceInfo &di, const float *scores, uint32_t n, uint32_t k, Workspace &ws, uint64_t *out_keys,
+                cudaStream_t s);
+int fill_uniform(void *out, int dtype, uint64_t n_rows, uint32_t dim, uint64_t seed, uint64_t row_base, cudaStream_t s);
+int gather_rows(const void *rows, int dtype, uint32_t dim, const uint32_t *idx, uint32_t n_idx, void *out,
+                cudaStream_t s);
+
+}  // namespace nk

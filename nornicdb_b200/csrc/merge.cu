@@ -1,0 +1,166 @@
+// merge.cu — candidate-list merge, key decoding, and device top-k over a precomputed score array.
+//
+// merge_keys is the "partial top-k merge" step of the path: per-CTA lists inside one GPU, and the
+// per-GPU lists of a row-sharded corpus.  It applies the same (score desc, row asc)
+// order as the scan, so the result does not depend on how rows were partitioned.
+// topk_scores replaces the host insertion sort of cuda_topk (pkg/gpu/cuda/cuda_bridge.go:327-375):
+// selection happens on the device and only k (index, score) pairs cross PCIe instead of n scores.
+#include "kernels.cuh"
+
+namespace nk {
+
+constexpr int MERGE_THREADS = 256;
+constexpr int MERGE_P = 2048;  // sort width; NK_MAX_K <= MERGE_P / 2
+
+struct MergeParams {
+    const uint64_t *keys;
+    uint32_t n_lists;
+    size_t list_stride, q_stride;
+    uint32_t k;
+    uint64_t *out;  // [Q][k]
+};
+
+// One CTA per query.  Streams the n_lists*k candidate keys through a 2048-wide sort buffer, keeping
+// the best k at the front after every round.  Keys below the current k-th best are dropped on load.
+__global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(MergeParams p) {
+    __shared__ uint64_t sbuf[MERGE_P];
+    __shared__ int s_fill;
+    const uint32_t q = blockIdx.x;
+    const uint64_t *base = p.keys + (size_t)q * p.q_stride;
+    const uint64_t total = (uint64_t)p.n_lists * p.k;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < MERGE_P; i += MERGE_THREADS) sbuf[i] = 0ull;
+    if (tid == 0) s_fill = 0;
+    __syncthreads();
+
+    uint64_t kth = 0;  // current k-th best key (0 = none yet)
+    uint64_t pos = 0;
+    while (pos < total) {
+        // fill slots [fill, MERGE_P) with keys that can still matter
+        const uint64_t room_all = MERGE_P - (uint64_t)s_fill;
+        __syncthreads();
+        const int fill0 = s_fill;
+        uint64_t chunk = total - pos;
+        if (chunk > room_all) chunk = room_all;
+        for (uint64_t i = tid; i < chunk; i += MERGE_THREADS) {
+            uint64_t g = pos + i;
+            uint32_t l = (uint32_t)(g / p.k), s = (uint32_t)(g - (uint64_t)l * p.k);
+            uint64_t key = base[(size_t)l * p.list_stride + s];
+            if (key > kth) {
+                int slot = atomicAdd(&s_fill, 1);
+                sbuf[slot] = key;
+            }
+        }
+        pos += chunk;
+        __syncthreads();
+        const int filled = s_fill;
+        // sort only when the buffer is nearly full or the input is exhausted
+        if (pos >= total || filled > MERGE_P - MERGE_THREADS) {
+            for (int i = filled + tid; i < MERGE_P; i += MERGE_THREADS) sbuf[i] = 0ull;
+            block_bitonic_sort_desc(sbuf, MERGE_P);
+            int keep = filled < (int)p.k ? filled : (int)p.k;
+            if (filled >= (int)p.k) kth = sbuf[p.k - 1];
+            __syncthreads();
+            if (tid == 0) s_fill = keep;
+            __syncthreads();
+        }
+        (void)fill0;
+    }
+    __syncthreads();
+    const int have = s_fill;
+    for (uint32_t i = tid; i < p.k; i += MERGE_THREADS) p.out[(size_t)q * p.k + i] = (int)i < have ? sbuf[i] : 0ull;
+}
+
+int merge_keys(const uint64_t *keys, uint32_t n_lists, size_t list_stride, size_t q_stride, uint32_t Q, uint32_t k,
+               uint64_t *out_keys, cudaStream_t stream) {
+    if (Q == 0 || k == 0) return 0;
+    if (k > MERGE_P / 2) {
+        set_error("merge: k=%u too large", k);
+        return -1;
+    }
+    MergeParams p{keys, n_lists, list_stride, q_stride, k, out_keys};
+    merge_keys_kernel<<<Q, MERGE_THREADS, 0, stream>>>(p);
+    NK_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+__global__ void decode_keys_kernel(const uint64_t *keys, size_t total, int metric, uint32_t *out_idx, float *out_score) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    uint64_t key = keys[i];
+    float s = key_score(key);
+    if (metric == NK_METRIC_EUCLIDEAN) s = sqrtf(fmaxf(-s, 0.0f));
+    out_idx[i] = key ? key_row(key) : 0xffffffffu;
+    out_score[i] = key ? s : 0.0f;
+}
+
+int decode_keys(const uint64_t *keys, uint32_t Q, uint32_t k, int metric, uint32_t *out_idx, float *out_score,
+                cudaStream_t stream) {
+    size_t total = (size_t)Q * k;
+    if (total == 0) return 0;
+    decode_keys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(keys, total, metric, out_idx, out_score);
+    NK_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device top-k over a score array (legacy cuda_topk).  Same threshold + buffer + prune scheme as the
+// fused scan, fed from memory instead of from the dot products.
+// ---------------------------------------------------------------------------------------------
+constexpr int TOPK_THREADS = 256;
+constexpr int TOPK_IV = 1024;  // scores per CTA between prune checks
+
+__global__ void __launch_bounds__(TOPK_THREADS) topk_scores_kernel(const float *scores, uint32_t n, uint32_t k, int P,
+                                                                   uint64_t *cand, uint64_t *partial, int *flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *sbuf = reinterpret_cast<uint64_t *>(smem_raw);
+    __shared__ float s_tau;
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) {
+        s_tau = -INFINITY;
+        s_cnt = 0;
+    }
+    __syncthreads();
+    uint64_t *my = cand + (size_t)blockIdx.x * P;
+    const uint32_t num_iv = (n + TOPK_IV - 1) / TOPK_IV;
+    for (uint32_t iv = blockIdx.x; iv < num_iv; iv += gridDim.x) {
+        for (uint32_t i = iv * TOPK_IV + threadIdx.x; i < (iv + 1) * TOPK_IV && i < n; i += TOPK_THREADS) {
+            float s = scores[i];
+            if (s != s) s = -INFINITY;
+            if (s >= s_tau) {
+                int pos = atomicAdd(&s_cnt, 1);
+                if (pos < P) my[pos] = make_key(s, i);
+                else atomicExch(flags, 1);
+            }
+        }
+        __syncthreads();
+        bool need = s_cnt > P - TOPK_IV;
+        __syncthreads();
+        if (need) block_prune(my, P, &s_cnt, &s_tau, k, sbuf, P);
+    }
+    block_prune(my, P, &s_cnt, &s_tau, k, sbuf, P);
+    for (uint32_t i = threadIdx.x; i < k; i += TOPK_THREADS) partial[(size_t)blockIdx.x * k + i] = sbuf[i];
+}
+
+int topk_scores(const DeviceInfo &di, const float *scores, uint32_t n, uint32_t k, Workspace &ws, uint64_t *out_keys,
+                cudaStream_t s) {
+    if (n == 0 || k == 0) return 0;
+    if (k > NK_MAX_K) {
+        set_error("k=%u exceeds NK_MAX_K=%u", k, NK_MAX_K);
+        return -1;
+    }
+    int P = (int)next_pow2(k + TOPK_IV + 1);
+    uint32_t num_iv = (n + TOPK_IV - 1) / TOPK_IV;
+    uint32_t grid = (uint32_t)di.num_sms * 2;
+    if (grid > num_iv) grid = num_iv;
+    if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)grid * P * 8)) return -1;
+    if (ws_reserve((void **)&ws.partial, &ws.partial_bytes, (size_t)grid * k * 8)) return -1;
+    size_t smem = (size_t)P * 8;
+    NK_CUDA_OK(cudaFuncSetAttribute(topk_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_scores_kernel<<<grid, TOPK_THREADS, smem, s>>>(scores, n, k, P, ws.cand, ws.partial, ws.flags);
+    NK_CUDA_OK(cudaGetLastError());
+    return merge_keys(ws.partial, grid, k, 0, 1, k, out_keys, s);
+}
+
+}  // namespace nk

@@ -1,0 +1,166 @@
+"""KnnIndex — thin host wrapper over the fused batched C ABI (nk_* in include/nornic_knn.h).
+
+This is the object gpu.EmbeddingIndex would hold instead of a cuda.Buffer (pkg/gpu/gpu.go:1224-1260): a
+row-major corpus resident in HBM, row-sharded across the GPUs of this process, searched Q queries at a
+time by one fused distance + top-k kernel per shard."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+
+METRICS = {"cosine": 0, "dot": 1, "euclidean": 2}
+DTYPES = {"f32": 0, "fp32": 0, "float32": 0, "f16": 1, "fp16": 1, "float16": 1}
+PATHS = {"auto": 0, "simt": 1, "tensor": 2}
+NK_MAX_K = 1024
+
+
+class KnnError(RuntimeError):
+    pass
+
+
+def _check(ret: int, what: str) -> int:
+    if ret < 0:
+        raise KnnError(f"{what}: {_lib.last_error()}")
+    return ret
+
+
+class KnnIndex:
+    def __init__(self, dim: int, metric: str = "cosine", dtype: str = "f32", devices: Sequence[int] = (0,)):
+        self.lib = _lib.load()
+        self.dim = int(dim)
+        self.metric = metric
+        self.dtype = DTYPES[dtype]
+        self.np_dtype = np.float16 if self.dtype == 1 else np.float32
+        self.devices = list(devices)
+        ids = (C.c_int * len(self.devices))(*self.devices)
+        self.ptr = self.lib.nk_index_create(ids, len(self.devices), self.dim, self.dtype, METRICS[metric])
+        if not self.ptr:
+            raise KnnError(f"nk_index_create: {_lib.last_error()}")
+
+    # -- lifecycle ---------------------------------------------------------------------------------
+    def release(self) -> None:
+        if self.ptr:
+            self.lib.nk_index_release(self.ptr)
+            self.ptr = None
+
+    close = release
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def __len__(self) -> int:
+        return int(self.lib.nk_index_rows(self.ptr))
+
+    # -- corpus ------------------------------------------------------------------------------------
+    def _rows(self, rows) -> np.ndarray:
+        a = np.ascontiguousarray(np.asarray(rows, dtype=self.np_dtype))
+        if a.size % self.dim:
+            raise KnnError("rows are not a multiple of dim")
+        return a.reshape(-1, self.dim)
+
+    def upload(self, rows) -> None:
+        a = self._rows(rows)
+        _check(self.lib.nk_index_upload(self.ptr, a.ctypes.data_as(C.c_void_p), a.shape[0]), "nk_index_upload")
+
+    def append(self, rows) -> None:
+        a = self._rows(rows)
+        _check(self.lib.nk_index_append(self.ptr, a.ctypes.data_as(C.c_void_p), a.shape[0]), "nk_index_append")
+
+    def update_row(self, row: int, vec) -> None:
+        a = self._rows(vec)
+        _check(self.lib.nk_index_update_row(self.ptr, int(row), a.ctypes.data_as(C.c_void_p)), "nk_index_update_row")
+
+    def remove_swap(self, row: int) -> None:
+        _check(self.lib.nk_index_remove_swap(self.ptr, int(row)), "nk_index_remove_swap")
+
+    def fill_uniform(self, n_rows: int, seed: int) -> None:
+        _check(self.lib.nk_index_fill_uniform(self.ptr, int(n_rows), int(seed)), "nk_index_fill_uniform")
+
+    def set_row_base(self, row_base: int) -> None:
+        _check(self.lib.nk_index_set_row_base(self.ptr, int(row_base)), "nk_index_set_row_base")
+
+    def attach_device_rows(self, dev_ptr: int, n_rows: int) -> None:
+        _check(self.lib.nk_index_attach_device_rows(self.ptr, int(dev_ptr), int(n_rows)), "nk_index_attach_device_rows")
+
+    def set_path(self, path: str) -> None:
+        _check(self.lib.nk_index_set_path(self.ptr, PATHS[path]), "nk_index_set_path")
+
+    def read_rows(self, row: int, n_rows: int) -> np.ndarray:
+        out = np.empty((n_rows, self.dim), dtype=self.np_dtype)
+        _check(self.lib.nk_index_read_rows(self.ptr, int(row), int(n_rows), out.ctypes.data_as(C.c_void_p)),
+               "nk_index_read_rows")
+        return out
+
+    def enable_timing(self, on: bool = True) -> None:
+        _check(self.lib.nk_index_enable_timing(self.ptr, 1 if on else 0), "nk_index_enable_timing")
+
+    def scan_time_ms(self) -> Tuple[float, int]:
+        ms, n = C.c_double(0), C.c_uint64(0)
+        _check(self.lib.nk_index_scan_time_ms(self.ptr, C.byref(ms), C.byref(n)), "nk_index_scan_time_ms")
+        return float(ms.value), int(n.value)
+
+    def stats(self) -> dict:
+        st = _lib.NkStats()
+        _check(self.lib.nk_index_stats(self.ptr, C.byref(st)), "nk_index_stats")
+        return {name: int(getattr(st, name)) for name, _ in st._fields_}
+
+    # -- search ------------------------------------------------------------------------------------
+    def search(self, queries, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """queries [Q x dim] fp32 host -> (idx [Q x k'] uint32, score [Q x k'] fp32), k' = min(k, N).
+        Euclidean scores are distances (ascending); cosine / dot are similarities (descending)."""
+        q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32))
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        if q.shape[1] != self.dim:
+            raise KnnError(f"invalid dimensions: query has {q.shape[1]}, index has {self.dim}")  # gpu.go:1533-1535
+        Q = q.shape[0]
+        k = int(k)
+        if k <= 0 or Q == 0:
+            return np.empty((Q, 0), np.uint32), np.empty((Q, 0), np.float32)
+        idx = np.empty((Q, k), dtype=np.uint32)
+        sc = np.empty((Q, k), dtype=np.float32)
+        ke = _check(self.lib.nk_search(self.ptr, q.ctypes.data_as(C.c_void_p), Q, k, idx.ctypes.data_as(C.c_void_p),
+                                       sc.ctypes.data_as(C.c_void_p)), "nk_search")
+        return idx[:, :ke], sc[:, :ke]
+
+    def search_device(self, q_ptr: int, Q: int, k: int, out_idx_ptr: int, out_score_ptr: int, stream: int = 0) -> int:
+        return _check(self.lib.nk_search_device(self.ptr, q_ptr, Q, k, out_idx_ptr, out_score_ptr, stream),
+                      "nk_search_device")
+
+    def search_keys_device(self, q_ptr: int, Q: int, k: int, out_keys_ptr: int, stream: int = 0) -> int:
+        return _check(self.lib.nk_search_keys_device(self.ptr, q_ptr, Q, k, out_keys_ptr, stream),
+                      "nk_search_keys_device")
+
+    def score_subset(self, query, rows: Sequence[int], k: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
+        q = np.ascontiguousarray(np.asarray(query, dtype=np.float32).reshape(-1))
+        if q.size != self.dim:
+            raise KnnError(f"invalid dimensions: query has {q.size}, index has {self.dim}")
+        r = np.ascontiguousarray(np.asarray(rows, dtype=np.uint32).reshape(-1))
+        kk = len(r) if k is None else min(int(k), len(r))
+        if kk <= 0:
+            return np.empty(0, np.uint32), np.empty(0, np.float32)
+        idx = np.empty(kk, dtype=np.uint32)
+        sc = np.empty(kk, dtype=np.float32)
+        ke = _check(self.lib.nk_score_subset(self.ptr, q.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p),
+                                             len(r), kk, idx.ctypes.data_as(C.c_void_p),
+                                             sc.ctypes.data_as(C.c_void_p)), "nk_score_subset")
+        return idx[:ke], sc[:ke]
+
+
+def merge_keys_device(device_id: int, keys_ptr: int, n_lists: int, Q: int, k: int, metric: str, out_idx_ptr: int,
+                      out_score_ptr: int, stream: int = 0) -> None:
+    _check(_lib.load().nk_merge_keys_device(device_id, keys_ptr, n_lists, Q, k, METRICS[metric], out_idx_ptr,
+                                            out_score_ptr, stream), "nk_merge_keys_device")
+
+
+def fill_uniform_device(device_id: int, out_ptr: int, n_rows: int, dim: int, seed: int, row_base: int = 0,
+                        stream: int = 0) -> None:
+    _check(_lib.load().nk_fill_uniform_device(device_id, out_ptr, n_rows, dim, seed, row_base, stream),
+           "nk_fill_uniform_device")
