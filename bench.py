@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — kNN queries/sec + achieved HBM GB/s of the fused distance+top-k path (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W                (default workload: "headline")
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...                          (the reference's CPU path, timed on host cores)
+
+A "step" = one batch of Q queries searched against the whole HBM-resident corpus (one pass of the hot path).
+Workload "headline" = BASELINE.json's metric shape: N=10M x d=1024 fp32, k=10, with configs[1]'s Q=64 cosine.
+Multi-GPU: the corpus is row-sharded over the ranks (rank g owns rows [g*N/G, (g+1)*N/G)), every rank scans its
+shard with the same fused kernel, the per-rank candidate lists (Q*k*8 B) are all-gathered over NCCL and merged
+with the same (score desc, row asc) rule — total work is fixed, so scaling is "strong".
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput (queries already in HBM), `e2e` = the
+same metric through the reference-facing C-ABI call with HOST buffers (H2D of the queries and D2H of the
+results inside the timed region).  `roofline` is for the dominant kernel (the scan), timed with CUDA events
+inside the library on the launching stream.  `cpu_baseline` = the oracle's AVX2 restatement of the
+reference's pkg/simd brute force timed on this box's host cores on a bounded sample (N=1, rank 0 only)."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N_total, dim, dtype, Q, k, metric, description)
+    "headline": (10_000_000, 1024, "f32", 64, 10, "cosine",
+                 "N=10M d=1024 fp32 Q=64 k=10 cosine (BASELINE.json metric shape: d=1024 N=10M k=10; Q/metric of configs[1])"),
+    "c2": (1_000_000, 1024, "f32", 64, 10, "cosine", "configs[1]: N=1M d=1024 (bge-m3) fp32 Q=64 k=10 cosine"),
+    "c3": (10_000_000, 1024, "f32", 1024, 100, "dot", "configs[2]: N=10M d=1024 fp32 Q=1024 k=100 inner-product"),
+    "c4": (10_000_000, 768, "f16", 1, 10, "euclidean", "configs[3]: N=10M d=768 fp16 Q=1 k=10 L2"),
+    "c1": (100_000, 128, "f32", 1, 10, "cosine", "configs[0]: N=100k d=128 fp32 Q=1 k=10 cosine"),
+    "q1": (10_000_000, 1024, "f32", 1, 10, "cosine", "N=10M d=1024 fp32 Q=1 k=10 cosine (single-query latency)"),
+}
+CORPUS_SEED, QUERY_SEED = 42, 1337
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
+    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tensor"])
+    ap.add_argument("--rows", type=int, default=0, help="override N_total (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic(workload: str, path: str):
+    """dram bytes per scan launch from the committed ncu --set full capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return d.get(f"{workload}:{path}", d.get(workload))
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_run(N_total, dim, dtype, Q, k, metric, steps, warmup, budget_s=20.0):
+    """The reference's CPU brute force (oracle/simd_baseline.c: AVX2+FMA kernels in the simd.Batch* loop shape +
+    bounded insertion top-k), all host threads, on a bounded sample of the workload.  Returns the JSON fields."""
+    import numpy as np
+    import oracle
+    oracle.build()
+    threads = oracle.max_threads()
+    # bounded sample: S rows of the same synthetic corpus, Qs of the same queries
+    S = min(N_total, 131072 if dim >= 512 else 1_000_000)
+    Qs = min(Q, 8)
+    rows = oracle.fill_uniform(S, dim, CORPUS_SEED, dtype="f16" if dtype == "f16" else "f32")
+    if dtype == "f16":
+        rows = rows.astype(np.float32)  # the reference has no fp16 path: widen once (pkg/simd is float32-only)
+    q = oracle.fill_uniform(Qs, dim, QUERY_SEED)
+    t_one = None
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        oracle.simd_knn(rows, q, k, metric, threads=threads)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+        if t_one is None:
+            t_one = dt
+        if sum(times) > budget_s and len(times) >= 3:
+            break
+    t = sum(times) / len(times)
+    # linear scan: time for the full corpus = t * N_total / S; queries/sec = Qs / that
+    qps_full = Qs / (t * (N_total / S))
+    return {
+        "value": qps_full, "unit": "queries/s", "cores": threads, "kind": "port",
+        "sample": (f"{Qs} queries x first {S} rows of the same synthetic corpus (d={dim}), {len(times)} timed passes, "
+                   f"{t * 1e3:.1f} ms/pass, scaled linearly to N={N_total}; AVX2+FMA -ffast-math restatement of "
+                   f"pkg/simd (vek32) + insertion top-k, OpenMP over rows with {threads} threads"),
+        "ms_per_pass": t * 1e3, "steps_timed": len(times),
+    }
+
+
+def main():
+    args = parse_args()
+    N_total, dim, dtype, Q, k, metric, desc = WORKLOADS[args.workload]
+    if args.rows:
+        N_total = args.rows
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    G = args.gpus
+    if world != G:
+        if world == 1 and G > 1:
+            print(f"bench.py: --gpus {G} needs torchrun with {G} ranks", file=sys.stderr)
+            sys.exit(2)
+        G = world
+    elem = 2 if dtype == "f16" else 4
+    config = {"workload": desc, "N": N_total, "dim": dim, "corpus_dtype": dtype, "Q": Q, "k": k, "metric": metric,
+              "sharding": f"row-range x{G}" if G > 1 else "single GPU",
+              "l2": "corpus shard per GPU >> 126 MB L2 (inputs larger than L2; no flush needed)"
+              if N_total // G * dim * elem > 512e6 else "L2 flushed between steps (256 MB memset)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(N_total, dim, dtype, Q, k, metric, args.steps, args.warmup)
+        line = {
+            "impl": "reference", "metric": "kNN queries/sec", "value": r["value"], "unit": "queries/s", "n_gpus": G,
+            "steps": r["steps_timed"], "warmup": args.warmup, "ms_per_step": r["ms_per_pass"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config,
+            "cpu_baseline": {"value": r["value"], "unit": "queries/s", "cores": r["cores"], "kind": r["kind"],
+                             "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import numpy as np
+    import torch
+    from nornicdb_b200 import build as knn_build
+    from nornicdb_b200 import cuda as ncuda
+    from nornicdb_b200.knn import KnnIndex, fill_uniform_device, merge_keys_device
+
+    if rank == 0 or local_rank == 0:
+        knn_build.build()
+    if not ncuda.IsAvailable():
+        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if G > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- corpus: this rank's row range, generated in HBM by the counter-based generator
+    lo, hi = N_total * rank // G, N_total * (rank + 1) // G
+    ix = KnnIndex(dim, metric=metric, dtype=dtype, devices=(local_rank,))
+    ix.set_path(args.path)
+    ix.set_row_base(lo)
+    ix.fill_uniform(hi - lo, CORPUS_SEED)
+    n_steps_total = args.warmup + args.steps
+    # ---- queries for every step, resident in HBM before the timed region (different block each step)
+    stream = torch.cuda.current_stream().cuda_stream
+    q_all = torch.empty((n_steps_total, Q, dim), dtype=torch.float32, device=dev)
+    fill_uniform_device(local_rank, q_all.data_ptr(), n_steps_total * Q, dim, QUERY_SEED, 0, stream)
+    out_idx = torch.empty((Q, k), dtype=torch.int32, device=dev)
+    out_score = torch.empty((Q, k), dtype=torch.float32, device=dev)
+    keys_local = torch.empty((Q, k), dtype=torch.int64, device=dev)
+    keys_all = torch.empty((G, Q, k), dtype=torch.int64, device=dev) if G > 1 else None
+    flush = None
+    if "flushed" in config["l2"]:
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def step_device(i):
+        qp = q_all[i].data_ptr()
+        if G == 1:
+            ix.search_device(qp, Q, k, out_idx.data_ptr(), out_score.data_ptr(), stream)
+        else:
+            ix.search_keys_device(qp, Q, k, keys_local.data_ptr(), stream)
+            dist.all_gather_into_tensor(keys_all.view(-1), keys_local.view(-1))
+            merge_keys_device(local_rank, keys_all.data_ptr(), G, Q, k, metric, out_idx.data_ptr(),
+                              out_score.data_ptr(), stream)
+
+    # ---- warm-up
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    launches0 = ix.stats()["kernel_launches"]
+    ix.enable_timing(True)
+    ix.scan_time_ms()
+
+    # ---- timed region: exactly K steps, CUDA events per step on the launching stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        if flush is not None:
+            flush.zero_()
+        ev[s][0].record()
+        step_device(args.warmup + s)
+        ev[s][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+    scan_ms, scan_launches = ix.scan_time_ms()
+    ix.enable_timing(False)
+    launches = ix.stats()["kernel_launches"] - launches0 + (2 * args.steps if G > 1 else 0)
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = Q * args.steps / (total_ms / 1e3)
+
+    # ---- e2e: the reference-facing call with HOST buffers (H2D queries + D2H results inside the timed region)
+    q_host = torch.empty((n_steps_total, Q, dim), dtype=torch.float32).pin_memory()
+    q_host.copy_(q_all.cpu())
+    res_idx_h = torch.empty((Q, k), dtype=torch.int32).pin_memory()
+    res_sc_h = torch.empty((Q, k), dtype=torch.float32).pin_memory()
+    q_np = q_host.numpy()
+
+    def step_e2e(i):
+        if G == 1:
+            gi, gs = ix.search(q_np[i], k)  # nk_search: H2D + fused scan + merge + D2H, synchronous
+            return gi
+        qd = q_host[i].to(dev, non_blocking=True)
+        ix.search_keys_device(qd.data_ptr(), Q, k, keys_local.data_ptr(), stream)
+        dist.all_gather_into_tensor(keys_all.view(-1), keys_local.view(-1))
+        merge_keys_device(local_rank, keys_all.data_ptr(), G, Q, k, metric, out_idx.data_ptr(), out_score.data_ptr(), stream)
+        res_idx_h.copy_(out_idx, non_blocking=True)
+        res_sc_h.copy_(out_score, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return res_idx_h
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for i in range(min(args.warmup, 3)):
+        step_e2e(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        step_e2e(args.warmup + (s % args.steps))
+    e1.record()
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    e2e_ms = max(e0.elapsed_time(e1), e2e_wall * 1e3)  # host-synchronous API: wall clock is the honest figure
+    if dist is not None:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = Q * e2e_steps / (e2e_ms / 1e3)
+
+    # ---- roofline of the dominant kernel (the scan): algorithmic bytes per launch / measured launch duration
+    peak, peak_src = load_peaks()
+    n_shard = hi - lo
+    algo_bytes_per_launch = n_shard * dim * elem  # every corpus byte once per launch
+    merge_launches_in_scan = args.steps  # scan_time brackets scan launches + the per-CTA list merge
+    scan_kernel_launches = max(scan_launches - merge_launches_in_scan, 1)
+    avg_launch_ms = scan_ms / scan_kernel_launches
+    achieved = algo_bytes_per_launch / (avg_launch_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": load_traffic(args.workload, args.path), "peak_source": peak_src,
+                "kernel": "knn_scan", "algorithmic_bytes_per_launch": algo_bytes_per_launch,
+                "avg_launch_ms": avg_launch_ms, "scan_launches_per_step": scan_kernel_launches / args.steps,
+                "scan_share_of_step": scan_ms / sum(step_ms)}
+
+    line = {
+        "metric": "kNN queries/sec", "value": value, "unit": "queries/s", "n_gpus": G, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32" if dtype == "f32" else "f16 corpus / f32 accumulate", "data": "synthetic",
+        "config": config, "hbm_gbs_whole_step": G * n_shard * dim * elem / (total_ms / args.steps / 1e3) / 1e9,
+        "roofline": roofline, "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": Q * dim * 4, "d2h_bytes_per_step": Q * k * 8,
+                "ms_per_step": e2e_ms / e2e_steps, "api": "nk_search (C ABI, host buffers)" if G == 1 else
+                "pinned host -> H2D -> nk_search_keys_device -> ncclAllGather -> nk_merge_keys_device -> D2H"},
+        "gpu_launches": int(launches), "path": args.path, "wall_s_timed_region": t_wall,
+    }
+    if G == 1 and rank == 0 and not args.no_cpu_baseline:
+        r = cpu_reference_run(N_total, dim, dtype, Q, k, metric, steps=5, warmup=1, budget_s=15.0)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "queries/s", "cores": r["cores"], "kind": r["kind"],
+                                "sample": r["sample"]}
+    if rank == 0:
+        print(json.dumps(line))
+    ix.release()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
