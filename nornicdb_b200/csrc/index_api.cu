@@ -122,7 +122,7 @@ static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uin
         s.timing.emplace_back(e0, e1);
         s.timing_launches.push_back(ix->stats.kernel_launches - l0);
     }
-    if (rc == 0) ix->stats.bytes_scanned += (uint64_t)s.n * ix->dim * ix->esz() * (use_tensor ? 1 : ((Q + 7) / 8));
+    if (rc == 0) ix->stats.bytes_scanned += (uint64_t)s.n * ix->dim * ix->esz() * (use_tensor ? ((Q + 63) / 64) : ((Q + 7) / 8));
     return rc;
 }
 
