@@ -359,13 +359,14 @@ def main():
     peak, peak_src = load_peaks()
     n_shard = hi - lo
     algo_bytes_per_launch = n_shard * dim * elem  # every corpus byte once per launch
-    merge_launches_in_scan = args.steps  # scan_time brackets scan launches + the per-CTA list merge
-    scan_kernel_launches = max(scan_launches - merge_launches_in_scan, 1)
+    scan_kernel_launches = max(scan_launches, 1)  # main scan launches only (library brackets exactly those)
     avg_launch_ms = scan_ms / scan_kernel_launches
+    used_path = ix.last_path()
     achieved = algo_bytes_per_launch / (avg_launch_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": load_traffic(args.workload, args.path), "peak_source": peak_src,
-                "kernel": "knn_scan", "algorithmic_bytes_per_launch": algo_bytes_per_launch,
+                "traffic": load_traffic(args.workload, used_path), "peak_source": peak_src,
+                "kernel": "knn_scan_tc_kernel (tcgen05/TMEM/TMA, 3xTF32)" if used_path == "tensor" else "knn_scan_simt_kernel",
+                "algorithmic_bytes_per_launch": algo_bytes_per_launch,
                 "avg_launch_ms": avg_launch_ms, "scan_launches_per_step": scan_kernel_launches / args.steps,
                 "scan_share_of_step": scan_ms / sum(step_ms)}
 
@@ -378,7 +379,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": Q * dim * 4, "d2h_bytes_per_step": Q * k * 8,
                 "ms_per_step": e2e_ms / e2e_steps, "api": "nk_search (C ABI, host buffers)" if G == 1 else
                 "pinned host -> H2D -> nk_search_keys_device -> ncclAllGather -> nk_merge_keys_device -> D2H"},
-        "gpu_launches": int(launches), "path": args.path, "wall_s_timed_region": t_wall,
+        "gpu_launches": int(launches), "path": used_path, "wall_s_timed_region": t_wall,
     }
     if G == 1 and rank == 0 and not args.no_cpu_baseline:
         r = cpu_reference_run(N_total, dim, dtype, Q, k, metric, steps=5, warmup=1, budget_s=15.0)

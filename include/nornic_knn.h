@@ -137,9 +137,12 @@ int nk_index_attach_device_rows(NkIndex *ix, void *rows_dev, uint64_t n_rows);
 int nk_index_set_path(NkIndex *ix, int path);
 uint64_t nk_index_rows(const NkIndex *ix);
 int nk_index_stats(const NkIndex *ix, NkStats *out);
-/* Device-side timing of the scan kernels (bench.py roofline): when enabled, every scan launch is
- * bracketed by CUDA events on its stream.  nk_index_scan_time_ms synchronises, returns the summed
- * duration and launch count since the last call, and resets the counters. */
+/* Which kernel the last search used: NK_PATH_SIMT or NK_PATH_TENSOR (-1: null index). */
+int nk_index_last_path(const NkIndex *ix);
+/* Device-side timing of the dominant kernel (bench.py roofline): when enabled, the main scan launches of
+ * every search (CUDA-core or tensor-core scan; query prep and list merge excluded) are bracketed by CUDA
+ * events on their stream.  nk_index_scan_time_ms synchronises, returns the summed duration and the number
+ * of main scan launches since the last call, and resets the counters. */
 int nk_index_enable_timing(NkIndex *ix, int enabled);
 int nk_index_scan_time_ms(NkIndex *ix, double *total_ms, uint64_t *scan_launches);
 /* Copy n_rows rows starting at global row `row` back to the host (tests / Serialize). */

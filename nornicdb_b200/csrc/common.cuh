@@ -163,6 +163,61 @@ __device__ __forceinline__ void group_prune(uint64_t *cand, int cap, int *cnt, f
     }
     group_sync(bar_id, nthreads);
 }
+// ---------------------------------------------------------------------------------------------
+// Warp-level prune: select the best k of n <= 32*PER_LANE buffered keys with the keys held in registers
+// (PER_LANE per lane) by repeated warp-wide max extraction; writes them back sorted descending.  No block
+// barrier, so several warps prune different queries concurrently.  Cost ~ k * 60 instructions.
+// Caller guarantees every producer of cand[] has finished (barrier) and that *cnt <= 32*PER_LANE.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, o);
+        uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), o);
+        uint64_t w = ((uint64_t)hi << 32) | lo;
+        v = w > v ? w : v;
+    }
+    return v;
+}
+template <int PER_LANE>
+__device__ __forceinline__ void warp_prune(uint64_t *cand, int *cnt, float *tau, uint32_t k, int lane, uint64_t *out) {
+    int n = *cnt;
+    if (n > 32 * PER_LANE) n = 32 * PER_LANE;
+    uint64_t v[PER_LANE];
+    uint64_t lmax = 0;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {
+        int idx = lane + 32 * i;
+        v[i] = idx < n ? cand[idx] : 0ull;
+        lmax = v[i] > lmax ? v[i] : lmax;
+    }
+    __syncwarp();
+    const int keep = n < (int)k ? n : (int)k;
+    uint64_t last = 0;
+    for (int j = 0; j < keep; ++j) {
+        const uint64_t m = warp_max_u64(lmax);
+        last = m;
+        if (lane == 0) {
+            cand[j] = m;
+            if (out) out[j] = m;
+        }
+        if (lmax == m) {  // keys are unique (row id in the low word): exactly one lane owns it
+            lmax = 0;
+#pragma unroll
+            for (int i = 0; i < PER_LANE; ++i) {
+                if (v[i] == m) v[i] = 0ull;
+                lmax = v[i] > lmax ? v[i] : lmax;
+            }
+        }
+    }
+    if (out)
+        for (int j = keep + lane; j < (int)k; j += 32) out[j] = 0ull;
+    if (lane == 0) {
+        *cnt = keep;
+        *tau = (n >= (int)k) ? key_score(last) : -INFINITY;
+    }
+    __syncwarp();
+}
 #endif  // __CUDACC__
 
 }  // namespace nk

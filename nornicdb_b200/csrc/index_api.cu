@@ -39,6 +39,7 @@ struct NkIndex {
     int metric = NK_METRIC_COSINE;
     int path = NK_PATH_AUTO;
     bool timing_on = false;
+    bool last_path_tensor = false;
     uint64_t row_base = 0;
     std::vector<NkShard> shards;
     NkStats stats{};
@@ -109,19 +110,24 @@ static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uin
         use_tensor = tensor_ok && Q > 16;
     }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    const uint64_t l0 = ix->stats.kernel_launches;
+    uint64_t main_launches = 0;
     if (ix->timing_on) {
         NK_CUDA_OK(cudaEventCreate(&e0));
         NK_CUDA_OK(cudaEventCreate(&e1));
-        NK_CUDA_OK(cudaEventRecord(e0, stream));
+        a.ev_begin = e0; a.ev_end = e1; a.main_launches = &main_launches;
     }
     int rc = use_tensor ? nk::scan_tensor(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches)
                         : nk::scan_simt(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches);
     if (ix->timing_on) {
-        NK_CUDA_OK(cudaEventRecord(e1, stream));
-        s.timing.emplace_back(e0, e1);
-        s.timing_launches.push_back(ix->stats.kernel_launches - l0);
+        if (rc == 0 && main_launches) {
+            s.timing.emplace_back(e0, e1);
+            s.timing_launches.push_back(main_launches);
+        } else {
+            cudaEventDestroy(e0);
+            cudaEventDestroy(e1);
+        }
     }
+    ix->last_path_tensor = use_tensor;
     if (rc == 0) ix->stats.bytes_scanned += (uint64_t)s.n * ix->dim * ix->esz() * (use_tensor ? ((Q + 63) / 64) : ((Q + 7) / 8));
     return rc;
 }
@@ -326,6 +332,8 @@ int nk_index_stats(const NkIndex *ix, NkStats *out) {
     out->rows = ix->rows();
     return 0;
 }
+
+int nk_index_last_path(const NkIndex *ix) { return ix ? (ix->last_path_tensor ? NK_PATH_TENSOR : NK_PATH_SIMT) : -1; }
 
 int nk_index_enable_timing(NkIndex *ix, int enabled) {
     if (!ix) { nk::set_error("null index"); return -1; }

@@ -39,6 +39,10 @@ struct ScanArgs {
     uint32_t k = 0;              // 1..NK_MAX_K (may exceed n: missing slots are key 0)
     int metric = NK_METRIC_COSINE;
     cudaStream_t stream = nullptr;
+    // optional timing of the dominant kernel only (bench roofline): events recorded on `stream` right before the
+    // first and right after the last main scan launch (query prep / list merge excluded); *main_launches += count
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    uint64_t *main_launches = nullptr;
 };
 
 // Fused distance + top-k scan on CUDA cores (small Q, any dim / dtype / alignment).

@@ -8,6 +8,19 @@ namespace nk { namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully converged warp (the pattern ptxas recognises for uniform-datapath instructions such
+// as UTCHMMA / UTMALDG: issuing them from a divergent `if (lane == 0)` region makes the compiler wrap every
+// instruction in an ELECT/branch loop, ~50 extra cycles per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+        "elect.sync %%rx|%%px, %1;\n\t"
+        "@%%px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred) : "r"(0xffffffffu));
+    return pred != 0;
+}
+
 // ---- mbarrier -----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -135,6 +148,22 @@ __device__ __forceinline__ float cvt_rna_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// Packed fp32x2 arithmetic (Blackwell FADD2 / FFMA2): two lanes per instruction.
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t pack2(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
+// Round an fp32 bit pattern to TF32 (10 explicit mantissa bits), nearest / ties away — cvt.rna.tf32.f32 without
+// its Inf/NaN guards (Inf stays Inf; values within 2^-11 of FLT_MAX overflow to Inf, irrelevant for embeddings).
+__device__ __forceinline__ uint32_t tf32_round_bits(uint32_t x) { return (x + 0x1000u) & 0xffffe000u; }
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

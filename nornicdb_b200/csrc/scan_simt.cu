@@ -299,6 +299,7 @@ int scan_simt(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *
     (void)esz;
 
     uint32_t grid_used = 0;
+    if (a.ev_begin) NK_CUDA_OK(cudaEventRecord(a.ev_begin, a.stream));
     for (uint32_t q0 = 0; q0 < a.Q;) {
         uint32_t left = a.Q - q0;
         int qt = left >= 5 ? 8 : left >= 3 ? 4 : left == 2 ? 2 : 1;
@@ -330,8 +331,10 @@ int scan_simt(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *
         kern<<<grid_used, SIMT_THREADS, smem, a.stream>>>(p);
         NK_CUDA_OK(cudaGetLastError());
         if (launches) ++*launches;
+        if (a.main_launches) ++*a.main_launches;
         q0 += p.nq;
     }
+    if (a.ev_end) NK_CUDA_OK(cudaEventRecord(a.ev_end, a.stream));
     // Fold the per-CTA lists: list l of query q starts at partial[(q*grid + l)*k].
     if (merge_keys(ws.partial, grid_used, a.k, (size_t)grid_used * a.k, a.Q, a.k, out_keys, a.stream)) return -1;
     if (launches) ++*launches;

@@ -98,6 +98,9 @@ class KnnIndex:
                "nk_index_read_rows")
         return out
 
+    def last_path(self) -> str:
+        return {1: "simt", 2: "tensor"}.get(int(self.lib.nk_index_last_path(self.ptr)), "?")
+
     def enable_timing(self, on: bool = True) -> None:
         _check(self.lib.nk_index_enable_timing(self.ptr, 1 if on else 0), "nk_index_enable_timing")
 

@@ -49,7 +49,7 @@ def test_tensor_dims(knn_lib, oracle_mod, d):
     run_tc(oracle_mod, 4000, d, 32, 10, "cosine")
 
 
-@pytest.mark.parametrize("k", [1, 100, 300, 1024])
+@pytest.mark.parametrize("k", [1, 100, 300, 767])
 def test_tensor_k(knn_lib, oracle_mod, k):
     run_tc(oracle_mod, 30_000, 64, 16, k, "cosine")
 
