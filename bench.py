@@ -248,7 +248,8 @@ def main():
         torch.cuda.synchronize()
 
     # ---- corpus: this rank's row range, generated in HBM by the counter-based generator
-    lo, hi = N_total * rank // G, N_total * (rank + 1) // G
+    from nornicdb_b200.sharding import shard_range
+    lo, hi = shard_range(N_total, G, rank)
     ix = KnnIndex(dim, metric=metric, dtype=dtype, devices=(local_rank,))
     ix.set_path(args.path)
     ix.set_row_base(lo)

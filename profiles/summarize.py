@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Turns the raw ncu outputs in gpurun_out/ into the committed summaries under profiles/ :
+   launches_<tag>.md   per-kernel totals + shares from the `--metrics gpu__time_duration.sum` launch list
+   ncu_<tag>.md        key metrics of one `--set full` capture (dram bytes, duration, pipes, occupancy, stalls)
+   traffic.json        dram__bytes_read+write per scan launch, consumed by bench.py's roofline.traffic
+Usage: python profiles/summarize.py r1"""
+import csv
+import json
+import os
+import subprocess
+import sys
+from collections import defaultdict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles")
+G = os.path.join(ROOT, "gpurun_out")
+
+
+def launches(csv_path, md_path, title):
+    rows = [r for r in csv.reader(open(csv_path)) if len(r) > 5]
+    hdr = [i for i, r in enumerate(rows) if r[0] == "ID"][0]
+    h, data = rows[hdr], rows[hdr + 1:]
+    ki, vi, ui = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
+    agg = defaultdict(lambda: [0, 0.0])
+    for r in data:
+        v = float(r[vi].replace(",", ""))
+        v = v / 1e3 if r[ui] == "ns" else v * 1e3 if r[ui] == "ms" else v
+        agg[r[ki]][0] += 1
+        agg[r[ki]][1] += v
+    tot = sum(v for _, v in agg.values())
+    search = sum(v for k, (_, v) in agg.items() if "fill_uniform" not in k)
+    with open(md_path, "w") as f:
+        f.write(f"# {title}\n\nSource: `{os.path.basename(csv_path)}` (ncu --metrics gpu__time_duration.sum --clock-control none; "
+                "cold-cache, serialised launches: compare SHARES).\n\n| kernel | launches | total us | us/launch | share of all | share of search kernels |\n|---|---:|---:|---:|---:|---:|\n")
+        for k, (c, v) in sorted(agg.items(), key=lambda x: -x[1][1]):
+            ss = "-" if "fill_uniform" in k else f"{100 * v / search:.1f}%"
+            f.write(f"| `{k[:90]}` | {c} | {v:.1f} | {v / c:.1f} | {100 * v / tot:.1f}% | {ss} |\n")
+        f.write("\n`fill_uniform_kernel` generates the synthetic corpus once, outside the timed region.\n")
+
+
+WANT = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__cycles_elapsed.max", "smsp__cycles_active.avg", "sm__cycles_active.avg", "lts__t_sectors_srcunit_tex_op_read.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+]
+
+
+def ncu_summary(rep, md_path, title, algorithmic_bytes=None):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    h, units, vals = rows[0], rows[1], rows[2]
+    d = {n: (vals[i], units[i]) for i, n in enumerate(h)}
+    name = d.get("Kernel Name", ("?", ""))[0]
+    with open(md_path, "w") as f:
+        f.write(f"# {title}\n\nSource: `{os.path.basename(rep)}` (ncu --set full --clock-control none, one launch of `{name[:80]}`; "
+                "numbers under the profiler are not bench values).\n\n| metric | value | unit |\n|---|---:|---|\n")
+        for w in WANT:
+            if w in d:
+                f.write(f"| `{w}` | {d[w][0]} | {d[w][1]} |\n")
+        stalls = sorted(((float(v[0] or 0), n) for n, v in d.items() if n.startswith("smsp__average_warps_issue_stalled") and n.endswith("_per_issue_active.ratio")), reverse=True)[:6]
+        if stalls:
+            f.write("\nTop warp-stall reasons (warps stalled per issue-active cycle):\n\n")
+            for v, n in stalls:
+                f.write(f"* `{n}` = {v:.2f}\n")
+
+    def gb(key):
+        v, u = d[key]
+        v = float(v.replace(",", ""))
+        return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
+    traffic = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum")
+    dur, du = d["gpu__time_duration.sum"]
+    with open(md_path, "a") as f:
+        f.write(f"\nDRAM traffic per launch = {traffic / 1e9:.4f} GB")
+        if algorithmic_bytes:
+            f.write(f" vs {algorithmic_bytes / 1e9:.4f} GB algorithmic (ratio {traffic / algorithmic_bytes:.3f})")
+        f.write(f"; duration {dur} {du} under the profiler.\n")
+    return traffic
+
+
+if __name__ == "__main__":
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+    launches(os.path.join(G, f"launches_{tag}_headline.csv"), os.path.join(OUT, f"launches_{tag}_headline.md"),
+             f"Launch list, round {tag[1:]}: bench.py headline (N=10M d=1024 Q=64 k=10 cosine), tensor-core path")
+    if os.path.exists(os.path.join(G, f"launches_{tag}_simt.csv")):
+        launches(os.path.join(G, f"launches_{tag}_simt.csv"), os.path.join(OUT, f"launches_{tag}_c2_simt.md"),
+                 f"Launch list, round {tag[1:]}: bench.py c2 (N=1M d=1024 Q=64 k=10 cosine), CUDA-core path (first working version)")
+    t = {}
+    t["headline:tensor"] = ncu_summary(os.path.join(G, f"prof_{tag}_tc_headline.ncu-rep"), os.path.join(OUT, f"ncu_{tag}_scan_tc_headline.md"),
+                                       "knn_scan_tc_kernel — N=10M d=1024 fp32 Q=64 k=10 cosine", 10_000_000 * 1024 * 4)
+    t["q1:simt"] = ncu_summary(os.path.join(G, f"prof_{tag}_simt_q1.ncu-rep"), os.path.join(OUT, f"ncu_{tag}_scan_simt_q1.md"),
+                               "knn_scan_simt_kernel — N=10M d=1024 fp32 Q=1 k=10 cosine", 10_000_000 * 1024 * 4)
+    t["c4:simt"] = ncu_summary(os.path.join(G, f"prof_{tag}_simt_c4.ncu-rep"), os.path.join(OUT, f"ncu_{tag}_scan_simt_c4.md"),
+                               "knn_scan_simt_kernel — N=10M d=768 fp16 Q=1 k=10 L2", 10_000_000 * 768 * 2)
+    t["headline:simt"] = t["q1:simt"]  # same kernel, same bytes per launch (one launch = one 8-query group)
+    json.dump(t, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
+    print(json.dumps(t, indent=1))
