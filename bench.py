@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
-    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tensor"])
+    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tensor", "filter"])
     ap.add_argument("--rows", type=int, default=0, help="override N_total (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -143,7 +143,8 @@ def cpu_reference_run(N_total, dim, dtype, Q, k, metric, steps, warmup, budget_s
     import numpy as np
     import oracle
     oracle.build()
-    hw = oracle.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1; the baseline sizes itself from the CPUs this process may run on
+    hw = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     # bounded sample: S rows of the same synthetic corpus, Qs of the same queries
     S = min(N_total, 131072 if dim >= 512 else 1_000_000)
     Qs = min(Q, 8)
@@ -188,6 +189,11 @@ def cpu_reference_run(N_total, dim, dtype, Q, k, metric, steps, warmup, budget_s
 
 def main():
     args = parse_args()
+    # torchrun exports OMP_NUM_THREADS=1 for every rank; the CPU baseline (oracle/liboracle.so, OpenMP) must be
+    # free to use every core this process may run on.  Must happen before libgomp initialises.
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(ncpu)
     N_total, dim, dtype, Q, k, metric, desc = WORKLOADS[args.workload]
     if args.rows:
         N_total = args.rows
@@ -366,7 +372,8 @@ def main():
     achieved = algo_bytes_per_launch / (avg_launch_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": load_traffic(args.workload, used_path), "peak_source": peak_src,
-                "kernel": "knn_scan_tc_kernel (tcgen05/TMEM/TMA, 3xTF32)" if used_path == "tensor" else "knn_scan_simt_kernel",
+                "kernel": {"tensor": "knn_scan_tc_kernel<3> (tcgen05/TMEM/TMA, 3xTF32 exact)",
+                           "filter": "knn_scan_tc_kernel<1> (tcgen05/TMEM/TMA, 1xTF32 filter + exact fp32 rescoring)"}.get(used_path, "knn_scan_simt_kernel"),
                 "algorithmic_bytes_per_launch": algo_bytes_per_launch,
                 "avg_launch_ms": avg_launch_ms, "scan_launches_per_step": scan_kernel_launches / args.steps,
                 "scan_share_of_step": scan_ms / sum(step_ms)}

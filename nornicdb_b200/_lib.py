@@ -67,6 +67,7 @@ SIGNATURES = {
     "nk_index_rows": (_u64, [_vp]),
     "nk_index_stats": (_i, [_vp, C.POINTER(NkStats)]),
     "nk_index_last_path": (_i, [_vp]),
+    "nk_index_debug_flags": (_i, [_vp, C.POINTER(C.c_int)]),
     "nk_index_enable_timing": (_i, [_vp, _i]),
     "nk_index_scan_time_ms": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "nk_index_read_rows": (_i, [_vp, _u64, _u64, _vp]),

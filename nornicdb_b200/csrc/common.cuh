@@ -179,8 +179,12 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
     }
     return v;
 }
+// margin_mode (tensor-core filter scan): keys carry UPPER bounds; after the k-th best everything whose bound is
+// still >= (k-th bound - margin2) is kept as well (it may beat the k-th once re-scored exactly), up to max_keep
+// entries, and tau = k-th bound - margin2.  Exact mode keeps exactly the best k and tau = k-th score.
 template <int PER_LANE>
-__device__ __forceinline__ void warp_prune(uint64_t *cand, int *cnt, float *tau, uint32_t k, int lane, uint64_t *out) {
+__device__ __forceinline__ void warp_prune(uint64_t *cand, int *cnt, float *tau, uint32_t k, int lane, uint64_t *out,
+                                           int out_len, bool margin_mode, float margin2, int max_keep) {
     int n = *cnt;
     if (n > 32 * PER_LANE) n = 32 * PER_LANE;
     uint64_t v[PER_LANE];
@@ -192,14 +196,18 @@ __device__ __forceinline__ void warp_prune(uint64_t *cand, int *cnt, float *tau,
         lmax = v[i] > lmax ? v[i] : lmax;
     }
     __syncwarp();
-    const int keep = n < (int)k ? n : (int)k;
-    uint64_t last = 0;
-    for (int j = 0; j < keep; ++j) {
+    const int limit = margin_mode ? (n < max_keep ? n : max_keep) : (n < (int)k ? n : (int)k);
+    float kth = -INFINITY;
+    int keep = 0;
+    for (int j = 0; j < limit; ++j) {
         const uint64_t m = warp_max_u64(lmax);
-        last = m;
+        if (m == 0ull) break;
+        if (j >= (int)k && key_score(m) < kth - margin2) break;  // margin mode only (exact mode stops at limit == k)
+        if (j == (int)k - 1) kth = key_score(m);
+        keep = j + 1;
         if (lane == 0) {
             cand[j] = m;
-            if (out) out[j] = m;
+            if (out && j < out_len) out[j] = m;
         }
         if (lmax == m) {  // keys are unique (row id in the low word): exactly one lane owns it
             lmax = 0;
@@ -211,10 +219,10 @@ __device__ __forceinline__ void warp_prune(uint64_t *cand, int *cnt, float *tau,
         }
     }
     if (out)
-        for (int j = keep + lane; j < (int)k; j += 32) out[j] = 0ull;
+        for (int j = keep + lane; j < out_len; j += 32) out[j] = 0ull;
     if (lane == 0) {
         *cnt = keep;
-        *tau = (n >= (int)k) ? key_score(last) : -INFINITY;
+        *tau = (n >= (int)k) ? kth - (margin_mode ? margin2 : 0.0f) : -INFINITY;
     }
     __syncwarp();
 }

@@ -17,6 +17,8 @@
 namespace nk {
 int scan_tensor(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *out_keys, uint64_t *launches);
 bool scan_tensor_supported(const DeviceInfo &di, const ScanArgs &a);
+int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *out_keys, uint64_t *launches);
+bool scan_tensor_filter_supported(const DeviceInfo &di, const ScanArgs &a);
 }
 
 struct NkShard {
@@ -39,7 +41,7 @@ struct NkIndex {
     int metric = NK_METRIC_COSINE;
     int path = NK_PATH_AUTO;
     bool timing_on = false;
-    bool last_path_tensor = false;
+    int last_path = NK_PATH_SIMT;
     uint64_t row_base = 0;
     std::vector<NkShard> shards;
     NkStats stats{};
@@ -97,18 +99,20 @@ static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uin
     nk::ScanArgs a;
     a.rows = s.rows; a.dtype = ix->dtype; a.n = (uint32_t)s.n; a.dim = ix->dim; a.row_base = s.base;
     a.queries = q_dev; a.Q = Q; a.k = k; a.metric = ix->metric; a.stream = stream;
-    bool tensor_ok = nk::scan_tensor_supported(s.di, a);
-    bool use_tensor = false;
-    if (ix->path == NK_PATH_TENSOR) {
-        if (!tensor_ok) {
-            nk::set_error("tensor path does not support this shape (dim=%u dtype=%d Q=%u k=%u)", ix->dim, ix->dtype, Q, k);
+    // AUTO: up to 16 queries the CUDA-core scan is already HBM-bound; above that the tensor-core
+    // filter scan (1xTF32 + exact rescoring) where it applies, else the exact 3xTF32 scan, else CUDA cores.
+    const bool tensor_ok = nk::scan_tensor_supported(s.di, a), filter_ok = nk::scan_tensor_filter_supported(s.di, a);
+    int use = NK_PATH_SIMT;
+    if (ix->path == NK_PATH_TENSOR || ix->path == NK_PATH_TENSOR_FILTER) {
+        if (!(ix->path == NK_PATH_TENSOR ? tensor_ok : filter_ok)) {
+            nk::set_error("tensor path does not support this shape (dim=%u dtype=%d metric=%d Q=%u k=%u)", ix->dim, ix->dtype, ix->metric, Q, k);
             return -1;
         }
-        use_tensor = true;
-    } else if (ix->path == NK_PATH_AUTO) {
-        // Below ~16 queries the CUDA-core scan is already HBM-bound (2*Q flop/byte*... see DESIGN.md).
-        use_tensor = tensor_ok && Q > 16;
+        use = ix->path;
+    } else if (ix->path == NK_PATH_AUTO && Q > 16) {
+        use = filter_ok ? NK_PATH_TENSOR_FILTER : tensor_ok ? NK_PATH_TENSOR : NK_PATH_SIMT;
     }
+    const bool use_tensor = use != NK_PATH_SIMT;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     uint64_t main_launches = 0;
     if (ix->timing_on) {
@@ -116,8 +120,9 @@ static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uin
         NK_CUDA_OK(cudaEventCreate(&e1));
         a.ev_begin = e0; a.ev_end = e1; a.main_launches = &main_launches;
     }
-    int rc = use_tensor ? nk::scan_tensor(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches)
-                        : nk::scan_simt(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches);
+    int rc = use == NK_PATH_TENSOR_FILTER ? nk::scan_tensor_filter(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches)
+             : use == NK_PATH_TENSOR      ? nk::scan_tensor(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches)
+                                          : nk::scan_simt(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches);
     if (ix->timing_on) {
         if (rc == 0 && main_launches) {
             s.timing.emplace_back(e0, e1);
@@ -127,7 +132,7 @@ static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uin
             cudaEventDestroy(e1);
         }
     }
-    ix->last_path_tensor = use_tensor;
+    ix->last_path = use;
     if (rc == 0) ix->stats.bytes_scanned += (uint64_t)s.n * ix->dim * ix->esz() * (use_tensor ? ((Q + 63) / 64) : ((Q + 7) / 8));
     return rc;
 }
@@ -319,7 +324,7 @@ int nk_index_attach_device_rows(NkIndex *ix, void *rows_dev, uint64_t n_rows) {
 }
 
 int nk_index_set_path(NkIndex *ix, int path) {
-    if (!ix || path < NK_PATH_AUTO || path > NK_PATH_TENSOR) { nk::set_error("bad path"); return -1; }
+    if (!ix || path < NK_PATH_AUTO || path > NK_PATH_TENSOR_FILTER) { nk::set_error("bad path"); return -1; }
     ix->path = path;
     return 0;
 }
@@ -333,7 +338,16 @@ int nk_index_stats(const NkIndex *ix, NkStats *out) {
     return 0;
 }
 
-int nk_index_last_path(const NkIndex *ix) { return ix ? (ix->last_path_tensor ? NK_PATH_TENSOR : NK_PATH_SIMT) : -1; }
+int nk_index_debug_flags(NkIndex *ix, int out[4]) {
+    if (!ix || !out || ix->shards.empty()) { nk::set_error("null argument"); return -1; }
+    NkShard &s = ix->shards[0];
+    NK_CUDA_OK(cudaSetDevice(s.device));
+    NK_CUDA_OK(cudaDeviceSynchronize());
+    NK_CUDA_OK(cudaMemcpy(out, s.ws.flags, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int nk_index_last_path(const NkIndex *ix) { return ix ? ix->last_path : -1; }
 
 int nk_index_enable_timing(NkIndex *ix, int enabled) {
     if (!ix) { nk::set_error("null index"); return -1; }

@@ -18,12 +18,13 @@ struct Workspace {
     uint64_t *cand = nullptr;     size_t cand_bytes = 0;     // [grid][QT][cap] candidate buffers
     uint64_t *partial = nullptr;  size_t partial_bytes = 0;  // [Q][grid][k] per-CTA sorted lists
     uint64_t *keys = nullptr;     size_t keys_bytes = 0;     // [Q][k] merged keys
+    uint64_t *keys2 = nullptr;    size_t keys2_bytes = 0;    // [Q][c_out] filter-mode candidates (by upper bound)
     float *queries = nullptr;     size_t queries_bytes = 0;  // staged queries (host API)
     uint32_t *out_idx = nullptr;  size_t out_idx_bytes = 0;
     float *out_score = nullptr;   size_t out_score_bytes = 0;
     float *qaux = nullptr;        size_t qaux_bytes = 0;     // tensor path: split / normalised queries
     float *rownorm = nullptr;     size_t rownorm_bytes = 0;  // tensor path: per-row inverse norms / sq norms
-    int *flags = nullptr;                                    // [0] = candidate-buffer overflow (must stay 0)
+    int *flags = nullptr;   // [0] candidate-buffer overflow (must stay 0), [1] filter-margin overflow, [2] max |x|^2 bits
     int release();
 };
 int ws_reserve(void **p, size_t *cur, size_t need);
@@ -43,6 +44,7 @@ struct ScanArgs {
     // first and right after the last main scan launch (query prep / list merge excluded); *main_launches += count
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     uint64_t *main_launches = nullptr;
+    const int *only_if = nullptr;  // CUDA-core scan as a device-side conditional fallback (runs only if *only_if != 0)
 };
 
 // Fused distance + top-k scan on CUDA cores (small Q, any dim / dtype / alignment).
@@ -50,9 +52,10 @@ struct ScanArgs {
 int scan_simt(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *out_keys, uint64_t *launches);
 
 // Merge n_lists sorted (or unsorted) key lists per query into the best k, sorted descending.
-// key(list l, query q, slot i) = keys[l*list_stride + q*q_stride + i].
+// key(list l, query q, slot i) = keys[l*list_stride + q*q_stride + i], i < list_len (0 = k).
+// only_if != nullptr: the kernel returns at once unless *only_if != 0 (device-side conditional fallback).
 int merge_keys(const uint64_t *keys, uint32_t n_lists, size_t list_stride, size_t q_stride, uint32_t Q, uint32_t k,
-               uint64_t *out_keys, cudaStream_t stream);
+               uint64_t *out_keys, cudaStream_t stream, const int *only_if = nullptr, uint32_t list_len = 0);
 // keys [Q][k] -> idx/score [Q][k]; euclidean decodes score = sqrt(-s).
 int decode_keys(const uint64_t *keys, uint32_t Q, uint32_t k, int metric, uint32_t *out_idx, float *out_score,
                 cudaStream_t stream);

@@ -18,16 +18,19 @@ struct MergeParams {
     size_t list_stride, q_stride;
     uint32_t k;
     uint64_t *out;  // [Q][k]
+    const int *only_if;
+    uint32_t list_len;  // entries per input list (may differ from the output k)
 };
 
 // One CTA per query.  Streams the n_lists*k candidate keys through a 2048-wide sort buffer, keeping
 // the best k at the front after every round.  Keys below the current k-th best are dropped on load.
 __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(MergeParams p) {
+    if (p.only_if && *p.only_if == 0) return;
     __shared__ uint64_t sbuf[MERGE_P];
     __shared__ int s_fill;
     const uint32_t q = blockIdx.x;
     const uint64_t *base = p.keys + (size_t)q * p.q_stride;
-    const uint64_t total = (uint64_t)p.n_lists * p.k;
+    const uint64_t total = (uint64_t)p.n_lists * p.list_len;
     const int tid = threadIdx.x;
 
     for (int i = tid; i < MERGE_P; i += MERGE_THREADS) sbuf[i] = 0ull;
@@ -45,7 +48,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(MergeParams p
         if (chunk > room_all) chunk = room_all;
         for (uint64_t i = tid; i < chunk; i += MERGE_THREADS) {
             uint64_t g = pos + i;
-            uint32_t l = (uint32_t)(g / p.k), s = (uint32_t)(g - (uint64_t)l * p.k);
+            uint32_t l = (uint32_t)(g / p.list_len), s = (uint32_t)(g - (uint64_t)l * p.list_len);
             uint64_t key = base[(size_t)l * p.list_stride + s];
             if (key > kth) {
                 int slot = atomicAdd(&s_fill, 1);
@@ -73,13 +76,13 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(MergeParams p
 }
 
 int merge_keys(const uint64_t *keys, uint32_t n_lists, size_t list_stride, size_t q_stride, uint32_t Q, uint32_t k,
-               uint64_t *out_keys, cudaStream_t stream) {
+               uint64_t *out_keys, cudaStream_t stream, const int *only_if, uint32_t list_len) {
     if (Q == 0 || k == 0) return 0;
     if (k > MERGE_P / 2) {
         set_error("merge: k=%u too large", k);
         return -1;
     }
-    MergeParams p{keys, n_lists, list_stride, q_stride, k, out_keys};
+    MergeParams p{keys, n_lists, list_stride, q_stride, k, out_keys, only_if, list_len ? list_len : k};
     merge_keys_kernel<<<Q, MERGE_THREADS, 0, stream>>>(p);
     NK_CUDA_OK(cudaGetLastError());
     return 0;

@@ -36,6 +36,7 @@ struct SimtParams {
     uint64_t *cand;      // [grid][QT][P]
     uint64_t *partial;   // [Q][grid][k]
     int *flags;
+    const int *only_if;  // device-side conditional fallback: run only if *only_if != 0
 };
 
 // ---- element loaders -------------------------------------------------------------------------
@@ -93,6 +94,7 @@ __device__ __forceinline__ void warp_reduce_scatter(float (&v)[V], int lane) {
 
 template <typename T, bool VEC, int QT, int R, bool EUCLID>
 __global__ void __launch_bounds__(SIMT_THREADS) knn_scan_simt_kernel(SimtParams p) {
+    if (p.only_if && *p.only_if == 0) return;
     using L = Lane<T, VEC>;
     constexpr int EPL = L::EPL;
     constexpr int CH = 32 * EPL;  // elements a warp covers per step
@@ -327,7 +329,7 @@ int scan_simt(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *
         SimtParams p;
         p.rows = a.rows; p.n = a.n; p.dim = a.dim; p.row_base = a.row_base;
         p.queries = a.queries; p.q0 = q0; p.nq = left < (uint32_t)qt ? left : (uint32_t)qt; p.k = a.k;
-        p.metric = a.metric; p.P = P; p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags;
+        p.metric = a.metric; p.P = P; p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = a.only_if;
         kern<<<grid_used, SIMT_THREADS, smem, a.stream>>>(p);
         NK_CUDA_OK(cudaGetLastError());
         if (launches) ++*launches;
@@ -336,7 +338,7 @@ int scan_simt(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *
     }
     if (a.ev_end) NK_CUDA_OK(cudaEventRecord(a.ev_end, a.stream));
     // Fold the per-CTA lists: list l of query q starts at partial[(q*grid + l)*k].
-    if (merge_keys(ws.partial, grid_used, a.k, (size_t)grid_used * a.k, a.Q, a.k, out_keys, a.stream)) return -1;
+    if (merge_keys(ws.partial, grid_used, a.k, (size_t)grid_used * a.k, a.Q, a.k, out_keys, a.stream, a.only_if)) return -1;
     if (launches) ++*launches;
     return 0;
 }

@@ -1,28 +1,36 @@
 // scan_tensor.cu — fused distance + top-k scan on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
 //
-// For Q > ~16 queries the CUDA-core scan stops being HBM-bound (fp32 FMA ridge is ~10 flop/byte, the
-// batch needs Q/2 flop/byte), so the Q x N^T contraction moves to tcgen05.mma.  fp32 inputs on the
-// tensor cores mean TF32 (10-bit mantissa), which cannot meet the 1e-4 / identical-index-set parity bar
-// by itself, so each product is the 3xTF32 split  x*q ~= xh*qh + xl*qh + xh*ql  (xh = rna_tf32(x),
-// xl = x - xh), which restores ~2^-21 relative accuracy per product with fp32 accumulation in TMEM.
+// For Q > ~16 queries the CUDA-core scan stops being HBM-bound (fp32 FMA ridge ~10 flop/byte, the batch needs
+// Q/2 flop/byte), so the Q x N^T contraction moves to tcgen05.mma.  fp32 inputs on tensor cores mean TF32
+// (10-bit mantissa), which by itself cannot meet "identical index sets, 1e-4".  Two modes (template NT):
+//
+//   NT = 3  "exact":  3xTF32 split  x*q ~= xl*qh + xh*ql + xh*qh  (xh = rn_tf32(x), xl = x - xh exactly),
+//           fp32 accumulation in TMEM, ~2^-21 relative per product.  Per-CTA exact top-k lists.
+//   NT = 1  "filter": ONE TF32 product per element (a third of the tensor work and energy — the chip is
+//           power-capped when HBM and the tensor pipes both run flat out) with a RIGOROUS error margin:
+//           |s_hat - s| <= c*|x|*|q|, c = 2^-10 + d*2^-22  (rounding of both operands + fp32 accumulation), so
+//           every row whose upper bound s_hat + B can still reach the running k-th best lower bound is kept.
+//           The few survivors (k + a handful) are re-scored EXACTLY in fp32 by rescore_kernel, so final
+//           scores/indices carry no TF32 error at all.  If a margin buffer overflows (adversarial near-ties) a flag
+//           is raised ON DEVICE and the NT=3 kernels — enqueued behind, early-exiting when the flag is clear —
+//           redo the search exactly.  No host round trip.
 //
 // One persistent CTA per SM, warp-specialised (16 warps):
-//   warp 0      TMA producer: corpus K-slabs [256 rows x 32 floats] (128B-swizzled) + the query slabs
-//               (pre-split hi/lo, [64 x 32 floats] each) into a 4-stage shared-memory ring;
-//   warps 4-11  "split" warps, one thread per corpus row: read the row's 128 B of the slab from shared
-//               memory (conflict-free thanks to the 128B swizzle), form xh / xl, accumulate |x|^2 on the
-//               side (cosine needs it - no separate norm pass over the corpus), and store xh / xl with
-//               tcgen05.st into a 2-stage TMEM ring: the corpus is the MMA's A operand FROM TENSOR MEMORY,
-//               so shared-memory bandwidth is spent once per corpus byte, not three times;
-//   warp 1      MMA issuer (one thread): per slab 2 M-tiles x 4 k-steps x 3 MMAs (M=128 rows, N=64 queries,
-//               K=8), D accumulates in TMEM (double-buffered per row tile);
-//   warps 12-15 epilogue: tcgen05.ld the [128 rows x 64 queries] accumulators (thread = corpus row),
-//               scale by 1/|x| for cosine, compare against each query's running threshold and append the
-//               few survivors to the per-(CTA, query) candidate buffers; prune with a bitonic sort when a
-//               buffer could overflow.  Distances never go to memory.
-// Per-CTA best-k lists are folded by merge_keys(), exactly like the CUDA-core scan.
+//   warp 0      TMA producer: corpus K-slabs [256 rows x 32 floats] (128B-swizzled), ring released by the split
+//               warps as soon as the slab is in registers (EVICT_FIRST);
+//   warp 3      TMA producer: query slabs (pre-rounded hi [+ lo], [64 x 32 floats] each, L2-resident, EVICT_LAST);
+//   warps 4-11  "split" warps, one thread per corpus row: conflict-free swizzled LDS.128, xh (and xl) with packed
+//               FADD2/FFMA2, |x|^2 on the side (no separate norm pass), tcgen05.st into a TMEM ring: the corpus is
+//               the MMA's A operand FROM TENSOR MEMORY (smem-operand MMAs of this shape are 1.5x slower, see
+//               profiles/experiments/mma_rate.cu);
+//   warps 1,2   MMA issuers, one per 128-row M-tile (tcgen05.mma.kind::tf32 M=128 N=64 K=8, accumulators in TMEM);
+//               two issuers because one warp's per-slab poll/fence/commit overhead lets the shallow MMA queue drain;
+//   warps 12-15 epilogue: tcgen05.ld the [128 rows x 64 queries] accumulator (thread = corpus row), release it,
+//               scale / bound, compare against each query's running threshold with a compact mask pass, append the
+//               few survivors; warp-level register top-k prune.  Distances never go to memory.
+// Per-CTA lists are folded by merge_keys().
 //
-// Algorithmic HBM traffic per launch: n*dim*4 (corpus, once) + small query re-reads served from L2.
+// Algorithmic HBM traffic per launch: n*dim*4 (corpus, once); query re-reads are served from L2.
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -36,112 +44,138 @@ constexpr int THREADS = 512;
 constexpr int ROWS = 256;        // corpus rows per tile (2 M-tiles of 128)
 constexpr int QT = 64;           // queries per launch (MMA N)
 constexpr int BK = 32;           // floats per K-slab = one 128-byte swizzle row
-constexpr int ASTAGES = 4;       // corpus-slab ring (freed by the split warps as soon as they have read it)
-constexpr int BSTAGES = 5;       // query-slab ring (freed when the MMAs that read it complete)
-constexpr int TSTAGES = 3;       // TMEM A-operand ring depth
+constexpr int ASTAGES = 4;       // corpus-slab smem ring
 constexpr int A_BYTES = ROWS * BK * 4;   // 32 KB
-constexpr int B_BYTES = QT * BK * 4;     // 8 KB (hi) + 8 KB (lo)
-constexpr int BST_BYTES = 2 * B_BYTES;              // hi + lo
-constexpr int RING_BYTES = ASTAGES * A_BYTES + BSTAGES * BST_BYTES;  // 160 KB + 48 KB
+constexpr int B_BYTES = QT * BK * 4;     // 8 KB per part
 constexpr int TMEM_COLS = 512;
-constexpr int ACC_COL = 0;       // [mtile] x 64 columns -> 128 columns (single-buffered, drained per M-tile)
-constexpr int A_COL = 128;       // [tstage][mtile][hi|lo] x 32 columns -> 384 columns
+constexpr int ACC_COL = 0;       // [mtile] x 64 columns (single-buffered, drained per M-tile)
+constexpr int A_COL = 128;       // TMEM A-operand ring: 384 columns
 constexpr int EPI_THREADS = 128;
 constexpr int EPI_BAR = 1;
 constexpr int SPLIT_WARP0 = 4, EPI_WARP0 = 12;
+constexpr int MAX_BSTAGES = 8, MAX_TSTAGES = 6;
+constexpr int P = 512;           // candidate buffer capacity per (CTA, query): warp_prune<16>
+constexpr float EUC_EPS = 4e-6f;  // fp32 rounding of |x|^2 + |q|^2 in the euclidean upper bound
+constexpr float EUC_KEEP = 1.0f - EUC_EPS;
+
+template <int NT> struct Cfg {
+    static constexpr int PARTS = NT == 3 ? 2 : 1;          // hi (+ lo)
+    static constexpr int BST_BYTES = PARTS * B_BYTES;
+    static constexpr int BSTAGES = NT == 3 ? 5 : 8;        // 80 KB / 64 KB
+    static constexpr int TSTAGES = NT == 3 ? 3 : 6;        // 128 / 64 TMEM columns per stage
+    static constexpr int RING_BYTES = ASTAGES * A_BYTES + BSTAGES * BST_BYTES;
+};
 
 struct Params {
     uint32_t n, dim, nslab;
     uint64_t row_base;
     uint32_t q0, nq, k;
     int metric;
-    int P;
-    uint64_t *cand;     // [grid][QT][P]
-    uint64_t *partial;  // [Q][grid][k]
-    int *flags;
-    int debug;  // timing experiments only (NK_TC_DEBUG): 1 = no split math, 2 = no MMA, 4 = no epilogue scoring, 8 = no TMEM stores
+    uint32_t k_emit;          // slots per (CTA, query) in `partial` (k for exact; k + margin room for filter)
+    float margin_c;           // filter mode: c in |s_hat - s| <= c |x| |q|
+    const float *qnorm;       // filter mode: |q| per query (1 for cosine), padded to a multiple of 64
+    uint64_t *cand;           // [grid][QT][P]
+    uint64_t *partial;        // [Q][grid][k_emit]
+    int *flags;               // [0] fatal buffer overflow, [1] filter-margin overflow (-> exact fallback), [2] max |x|^2 bits
+    const int *only_if;       // exact fallback: run only if *only_if != 0
+    int debug;                // NK_TC_DEBUG bit 64: clock64 wait-time instrumentation of CTA 0
 };
 
 struct __align__(8) Shared {
-    uint64_t afull_s[ASTAGES], aempty_s[ASTAGES];  // corpus slab in smem: TMA -> split warps -> TMA
-    uint64_t bfull[BSTAGES], bempty[BSTAGES];      // query slabs in smem: TMA -> MMA -> TMA
-    uint64_t afull[TSTAGES][2], aempty[TSTAGES][2];  // per (TMEM stage, M-tile)
-    uint64_t accfull[2], accempty[2];                // per M-tile
+    uint64_t afull_s[ASTAGES], aempty_s[ASTAGES];    // corpus slab in smem: TMA -> split warps -> TMA
+    uint64_t bfull[MAX_BSTAGES], bempty[MAX_BSTAGES];  // query slabs in smem: TMA -> MMA -> TMA
+    uint64_t afull[MAX_TSTAGES][2], aempty[MAX_TSTAGES][2];  // A operand in TMEM, per (stage, M-tile)
+    uint64_t accfull[2], accempty[2];                // accumulators, per M-tile
     uint32_t tmem_base;
+    unsigned int maxxx;       // running max of |x|^2 (float bits) over the rows this CTA has scored
     float xx[2][ROWS];
     float tau[QT];
+    float qn[QT];
     int cnt[QT];
 };
 }  // namespace tc
 
+// Filter mode: 2 x (largest possible gap between an upper bound and the true score) for rows with |x|^2 <= maxxx.
+//   cosine 2c | dot 2c|x||q| | euclidean (on -dist^2) 2(2c|x||q| + eps(|x|^2+|q|^2))
+__device__ __forceinline__ float filter_margin2(int metric, float c, float maxxx, float qn) {
+    if (metric == NK_METRIC_COSINE) return 2.0f * c;
+    const float xq = sqrtf(maxxx) * qn;
+    if (metric == NK_METRIC_DOT) return 2.0f * c * xq;
+    return 2.0f * (2.0f * c * xq + tc::EUC_EPS * (maxxx + qn * qn));
+}
+
 // Wait-time instrumentation (NK_TC_DEBUG bit 64): cycles CTA 0 spends blocked at each hand-off.
 __device__ long long g_tc_prof[32];
-__device__ unsigned long long g_tc_cta_ns[2][160];  // [0] = start, [1] = end (globaltimer) per CTA
-__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TC_PROF_BEGIN() long long _t0 = prof ? clock64() : 0
 #define TC_PROF_END(slot) do { if (prof) { long long _t1 = clock64(); acc_##slot += _t1 - _t0; } } while (0)
 
-// Queries -> (optionally normalised) tf32 hi / lo arrays, zero padded to a multiple of 64 rows.
-__global__ void tc_prep_queries_kernel(const float *q, uint32_t Q, uint32_t Qpad, uint32_t dim, int normalise,
-                                       float *qhi, float *qlo) {
-    uint32_t row = blockIdx.x;
-    float inv = 1.0f;
-    if (row < Q && normalise) {
+// Queries -> tf32 hi (/ lo) arrays, zero padded to a multiple of 64 rows; cosine normalises first; also |q|.
+__global__ void tc_prep_queries_kernel(const float *q, uint32_t Q, uint32_t dim, int normalise, float *qhi, float *qlo,
+                                       float *qnorm) {
+    const uint32_t row = blockIdx.x;
+    __shared__ float red[32];
+    float t = 0.0f;
+    if (row < Q) {
         float a = 0.0f;
         for (uint32_t j = threadIdx.x; j < dim; j += blockDim.x) a = fmaf(q[(size_t)row * dim + j], q[(size_t)row * dim + j], a);
-        __shared__ float red[32];
 #pragma unroll
         for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
         __syncthreads();
-        float t = 0.0f;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-        inv = t > 0.0f ? 1.0f / sqrtf(t) : 0.0f;  // zero query -> all scores 0 (simd_amd64.go:31-35)
     }
+    const float nrm = sqrtf(t);
+    // zero query -> all cosine scores 0 (simd_amd64.go:31-35)
+    const float inv = normalise ? (t > 0.0f ? 1.0f / nrm : 0.0f) : 1.0f;
+    if (threadIdx.x == 0 && qnorm) qnorm[row] = normalise ? (t > 0.0f ? 1.0f : 0.0f) : nrm;
     for (uint32_t j = threadIdx.x; j < dim; j += blockDim.x) {
         float v = row < Q ? q[(size_t)row * dim + j] * inv : 0.0f;
-        float h = ptx::cvt_rna_tf32(v);
+        float h = __uint_as_float(ptx::tf32_round_bits(__float_as_uint(v)));
         qhi[(size_t)row * dim + j] = h;
-        qlo[(size_t)row * dim + j] = v - h;
+        if (qlo) qlo[(size_t)row * dim + j] = v - h;
     }
-    (void)Qpad;
 }
 
+template <int NT>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_qhi,
                    const __grid_constant__ CUtensorMap map_qlo, tc::Params p) {
     using namespace tc;
+    using C = Cfg<NT>;
+    constexpr bool FILTER = NT == 1;
+    if (p.only_if && *p.only_if == 0) return;  // exact fallback not needed (uniform over the grid)
+
     extern __shared__ unsigned char smem_dyn[];
     // 128-byte-swizzled tiles need 1024-byte alignment: align by hand (the launch reserves the slack).
     unsigned char *smem_raw = smem_dyn + ((1024u - (ptx::smem_u32(smem_dyn) & 1023u)) & 1023u);
-    // layout: [ASTAGES x A 32K] [BSTAGES x (Bhi 8K | Blo 8K)] [sort buffer P x 8] [Shared]
+    // layout: [ASTAGES x A 32K] [BSTAGES x (Bhi 8K [| Blo 8K])] [Shared]
     unsigned char *a_base = smem_raw;
     unsigned char *b_base = smem_raw + (size_t)ASTAGES * A_BYTES;
-    uint64_t *sbuf = reinterpret_cast<uint64_t *>(smem_raw + (size_t)RING_BYTES);
-    Shared &sh = *reinterpret_cast<Shared *>(smem_raw + (size_t)RING_BYTES + (size_t)p.P * 8);
+    Shared &sh = *reinterpret_cast<Shared *>(smem_raw + (size_t)C::RING_BYTES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t num_tiles = (p.n + ROWS - 1) / ROWS;
     const bool prof = (p.debug & 64) && blockIdx.x == 0;
     long long acc_a = 0, acc_b = 0, acc_c = 0, acc_d = 0;
     const long long t_start = prof ? clock64() : 0;
-    if ((p.debug & 64) && tid == 0 && blockIdx.x < 160) g_tc_cta_ns[0][blockIdx.x] = globaltimer_ns();
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_rows);
         ptx::prefetch_tensormap(&map_qhi);
-        ptx::prefetch_tensormap(&map_qlo);
+        if (NT == 3) ptx::prefetch_tensormap(&map_qlo);
         for (int i = 0; i < ASTAGES; ++i) { ptx::mbar_init(&sh.afull_s[i], 1); ptx::mbar_init(&sh.aempty_s[i], 8); }
-        for (int i = 0; i < BSTAGES; ++i) { ptx::mbar_init(&sh.bfull[i], 1); ptx::mbar_init(&sh.bempty[i], 2); }
-        for (int i = 0; i < TSTAGES; ++i)
+        for (int i = 0; i < C::BSTAGES; ++i) { ptx::mbar_init(&sh.bfull[i], 1); ptx::mbar_init(&sh.bempty[i], 2); }
+        for (int i = 0; i < C::TSTAGES; ++i)
             for (int m = 0; m < 2; ++m) { ptx::mbar_init(&sh.afull[i][m], 4); ptx::mbar_init(&sh.aempty[i][m], 1); }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&sh.accfull[i], 1); ptx::mbar_init(&sh.accempty[i], 4); }
+        sh.maxxx = 0u;
         ptx::fence_barrier_init();
     }
     if (warp == 2) ptx::tmem_alloc(&sh.tmem_base, TMEM_COLS);
     if (tid < QT) {
         sh.tau[tid] = -INFINITY;
         sh.cnt[tid] = 0;
+        sh.qn[tid] = (FILTER && p.qnorm) ? p.qnorm[p.q0 + tid] : 1.0f;
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -168,13 +202,13 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
         uint32_t g = 0;
         for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             for (uint32_t j = 0; j < p.nslab; ++j, ++g) {
-                const uint32_t s = g % BSTAGES;
-                { TC_PROF_BEGIN(); ptx::mbar_wait(&sh.bempty[s], ((g / BSTAGES) & 1) ^ 1); TC_PROF_END(a); }
+                const uint32_t s = g % C::BSTAGES;
+                { TC_PROF_BEGIN(); ptx::mbar_wait(&sh.bempty[s], ((g / C::BSTAGES) & 1) ^ 1); TC_PROF_END(a); }
                 if (ptx::elect_one_sync()) {
-                    unsigned char *st = b_base + (size_t)s * BST_BYTES;
-                    ptx::mbar_arrive_expect_tx(&sh.bfull[s], BST_BYTES);
+                    unsigned char *st = b_base + (size_t)s * C::BST_BYTES;
+                    ptx::mbar_arrive_expect_tx(&sh.bfull[s], C::BST_BYTES);
                     ptx::tma_load_2d(&map_qhi, &sh.bfull[s], st, (int32_t)(j * BK), (int32_t)p.q0, ptx::CACHE_EVICT_LAST);
-                    ptx::tma_load_2d(&map_qlo, &sh.bfull[s], st + B_BYTES, (int32_t)(j * BK), (int32_t)p.q0, ptx::CACHE_EVICT_LAST);
+                    if (NT == 3) ptx::tma_load_2d(&map_qlo, &sh.bfull[s], st + B_BYTES, (int32_t)(j * BK), (int32_t)p.q0, ptx::CACHE_EVICT_LAST);
                 }
                 __syncwarp();
             }
@@ -182,39 +216,40 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
         if (prof && lane == 0) { g_tc_prof[2] = acc_a; }
     } else if (warp == 1 || warp == 2) {
         // ===================================== MMA issuers (one warp per M-tile) ==================
-        // Two issuing warps: the per-slab serial overhead of one (barrier polls, fences, commits) overlaps with
-        // the other's MMAs, so the shallow tcgen05 queue never drains.  tcgen05.commit is per issuing thread.
-        {
-            const uint32_t m = warp - 1;
-            const uint32_t idesc = ptx::make_idesc_tf32(128, QT);
-            const uint32_t d = tmem + ACC_COL + m * QT;
-            uint32_t g = 0, it = 0;
-            for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-                for (uint32_t j = 0; j < p.nslab; ++j, ++g) {
-                    const uint32_t s = g % BSTAGES, ts = g % TSTAGES;
-                    if (j == 0) { TC_PROF_BEGIN(); ptx::mbar_wait(&sh.accempty[m], (it & 1) ^ 1); TC_PROF_END(b); }  // epilogue drained
-                    { TC_PROF_BEGIN(); ptx::mbar_wait(&sh.bfull[s], (g / BSTAGES) & 1); TC_PROF_END(a); }  // query slabs landed
-                    { TC_PROF_BEGIN(); ptx::mbar_wait(&sh.afull[ts][m], (g / TSTAGES) & 1); TC_PROF_END(c); }  // xh / xl are in TMEM
-                    ptx::tc_fence_after();
-                    if (ptx::elect_one_sync()) {
-                        const uint32_t bhi = ptx::smem_u32(b_base + (size_t)s * BST_BYTES);
-                        const uint64_t dhi = ptx::make_smem_desc_sw128(bhi), dlo = ptx::make_smem_desc_sw128(bhi + B_BYTES);
-                        const uint32_t ahi = tmem + A_COL + ((ts * 2 + m) * 2) * BK, alo = ahi + BK;
-                        if (!(p.debug & 2)) {
+        const uint32_t m = warp - 1;
+        const uint32_t idesc = ptx::make_idesc_tf32(128, QT);
+        const uint32_t d = tmem + ACC_COL + m * QT;
+        uint32_t g = 0, it = 0;
+        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (uint32_t j = 0; j < p.nslab; ++j, ++g) {
+                const uint32_t s = g % C::BSTAGES, ts = g % C::TSTAGES;
+                if (j == 0) { TC_PROF_BEGIN(); ptx::mbar_wait(&sh.accempty[m], (it & 1) ^ 1); TC_PROF_END(b); }  // epilogue drained
+                { TC_PROF_BEGIN(); ptx::mbar_wait(&sh.bfull[s], (g / C::BSTAGES) & 1); TC_PROF_END(a); }  // query slabs landed
+                { TC_PROF_BEGIN(); ptx::mbar_wait(&sh.afull[ts][m], (g / C::TSTAGES) & 1); TC_PROF_END(c); }  // A operand in TMEM
+                ptx::tc_fence_after();
+                if (ptx::elect_one_sync()) {
+                    const uint32_t bhi = ptx::smem_u32(b_base + (size_t)s * C::BST_BYTES);
+                    const uint64_t dhi = ptx::make_smem_desc_sw128(bhi);
+                    const uint32_t ahi = tmem + A_COL + (ts * 2 + m) * C::PARTS * BK;
+                    // K advance per MMA = 8 floats = 32 B = 2 descriptor units = 8 TMEM columns
+                    if (NT == 3) {
+                        const uint64_t dlo = ptx::make_smem_desc_sw128(bhi + B_BYTES);
+                        const uint32_t alo = ahi + BK;
 #pragma unroll
-                            for (uint32_t kk = 0; kk < BK / 8; ++kk) {
-                                // smallest terms first; K advance = 8 floats = 32 B = 2 descriptor units / 8 TMEM columns
-                                ptx::mma_tf32_ts(d, alo + kk * 8, dhi + kk * 2, idesc, (j | kk) != 0);
-                                ptx::mma_tf32_ts(d, ahi + kk * 8, dlo + kk * 2, idesc, 1);
-                                ptx::mma_tf32_ts(d, ahi + kk * 8, dhi + kk * 2, idesc, 1);
-                            }
+                        for (uint32_t kk = 0; kk < BK / 8; ++kk) {  // smallest terms first
+                            ptx::mma_tf32_ts(d, alo + kk * 8, dhi + kk * 2, idesc, (j | kk) != 0);
+                            ptx::mma_tf32_ts(d, ahi + kk * 8, dlo + kk * 2, idesc, 1);
+                            ptx::mma_tf32_ts(d, ahi + kk * 8, dhi + kk * 2, idesc, 1);
                         }
-                        ptx::tc_commit(&sh.aempty[ts][m]);                        // TMEM A slot of this M-tile reusable
-                        ptx::tc_commit(&sh.bempty[s]);                            // query slabs: both issuers must be done
-                        if (j + 1 == p.nslab) ptx::tc_commit(&sh.accfull[m]);     // accumulator of this M-tile complete
+                    } else {
+#pragma unroll
+                        for (uint32_t kk = 0; kk < BK / 8; ++kk) ptx::mma_tf32_ts(d, ahi + kk * 8, dhi + kk * 2, idesc, (j | kk) != 0);
                     }
-                    __syncwarp();
+                    ptx::tc_commit(&sh.aempty[ts][m]);                        // TMEM A slot of this M-tile reusable
+                    ptx::tc_commit(&sh.bempty[s]);                            // query slabs: both issuers must be done
+                    if (j + 1 == p.nslab) ptx::tc_commit(&sh.accfull[m]);     // accumulator of this M-tile complete
                 }
+                __syncwarp();
             }
         }
         if (prof && lane == 0 && warp == 1) { g_tc_prof[4] = acc_a; g_tc_prof[5] = acc_b; g_tc_prof[6] = acc_c; g_tc_prof[7] = clock64() - t_start; }
@@ -227,7 +262,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
         for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             uint64_t xx2 = 0;  // two partial sums of |x|^2 (packed f32x2)
             for (uint32_t j = 0; j < p.nslab; ++j, ++g) {
-                const uint32_t s = g % ASTAGES, ts = g % TSTAGES;
+                const uint32_t s = g % ASTAGES, ts = g % C::TSTAGES;
                 { TC_PROF_BEGIN(); ptx::mbar_wait(&sh.afull_s[s], (g / ASTAGES) & 1); TC_PROF_END(a); }
                 long long _tw = prof ? clock64() : 0;
                 const unsigned char *rowp = a_base + (size_t)s * A_BYTES + (size_t)r * 128;
@@ -241,28 +276,27 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                     for (int u = 0; u < 4; u += 2) {
                         const uint32_t h0 = ptx::tf32_round_bits(e[u]), h1 = ptx::tf32_round_bits(e[u + 1]);
                         const uint64_t x2 = ptx::pack2(e[u], e[u + 1]);
-                        const uint64_t l2 = ptx::sub_f32x2(x2, ptx::pack2(h0, h1));  // exact residual x - xh
-                        xx2 = ptx::fma_f32x2(x2, x2, xx2);                           // |x|^2 on the side (cosine)
+                        xx2 = ptx::fma_f32x2(x2, x2, xx2);  // |x|^2 on the side
                         hi[c * 4 + u] = h0; hi[c * 4 + u + 1] = h1;
-                        lo[c * 4 + u] = (uint32_t)l2; lo[c * 4 + u + 1] = (uint32_t)(l2 >> 32);
+                        if (NT == 3) {
+                            const uint64_t l2 = ptx::sub_f32x2(x2, ptx::pack2(h0, h1));  // exact residual x - xh
+                            lo[c * 4 + u] = (uint32_t)l2; lo[c * 4 + u + 1] = (uint32_t)(l2 >> 32);
+                        }
                     }
                 }
                 // the slab now lives in registers: hand the smem slot straight back to the TMA producer
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&sh.aempty_s[s]);
                 if (prof) acc_c += clock64() - _tw;
-                { TC_PROF_BEGIN(); ptx::mbar_wait(&sh.aempty[ts][m], ((g / TSTAGES) & 1) ^ 1); TC_PROF_END(b); }
+                { TC_PROF_BEGIN(); ptx::mbar_wait(&sh.aempty[ts][m], ((g / C::TSTAGES) & 1) ^ 1); TC_PROF_END(b); }
                 _tw = prof ? clock64() : 0;
                 ptx::tc_fence_after();
-                const uint32_t acol = tmem + lane_base + A_COL + ((ts * 2 + m) * 2) * BK;
-                if (!(p.debug & 8)) {
-                    ptx::tmem_st_32x32b_x32(acol, hi);
-                    ptx::tmem_st_32x32b_x32(acol + BK, lo);
-                    ptx::tmem_wait_st();
-                } else if (hi[0] == 0x12345678u && lo[3] == 77u) {
-                    sh.xx[0][r] = 1.0f;
-                }
-                if (j + 1 == p.nslab) sh.xx[it & 1][r] = __uint_as_float((uint32_t)xx2) + __uint_as_float((uint32_t)(xx2 >> 32));  // published by the afull arrive below
+                const uint32_t acol = tmem + lane_base + A_COL + (ts * 2 + m) * C::PARTS * BK;
+                ptx::tmem_st_32x32b_x32(acol, hi);
+                if (NT == 3) ptx::tmem_st_32x32b_x32(acol + BK, lo);
+                ptx::tmem_wait_st();
+                if (j + 1 == p.nslab)  // published by the afull arrive below
+                    sh.xx[it & 1][r] = __uint_as_float((uint32_t)xx2) + __uint_as_float((uint32_t)(xx2 >> 32));
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&sh.afull[ts][m]);
@@ -273,10 +307,12 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
         if (prof && lane == 0 && warp == SPLIT_WARP0 + 4) { g_tc_prof[13] = acc_a; g_tc_prof[14] = acc_b; g_tc_prof[15] = acc_c; g_tc_prof[16] = acc_d; }
     } else if (warp >= EPI_WARP0) {
         // ===================================== epilogue =========================================
-        const uint32_t quad = warp & 3, gtid = tid - EPI_WARP0 * 32;
+        const uint32_t quad = warp & 3;
         const uint32_t lane_base = (quad * 32u) << 16;
-        uint64_t *my_cand = p.cand + (size_t)blockIdx.x * QT * p.P;
-        const int prune_at = p.P - ROWS;
+        uint64_t *my_cand = p.cand + (size_t)blockIdx.x * QT * P;
+        const int prune_at = P - ROWS;
+        const bool cosine = p.metric == NK_METRIC_COSINE, euclid = p.metric == NK_METRIC_EUCLIDEAN;
+        const float bfac = p.margin_c * (euclid ? 2.0f : 1.0f);  // bound on -dist^2 = -(|x|^2+|q|^2-2x.q) is 2c|x||q|
         uint32_t it = 0;
         for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
 #pragma unroll 1
@@ -293,20 +329,37 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&sh.accempty[m]);
-                float scale = 1.0f;
-                if (p.metric == NK_METRIC_COSINE) {
-                    float x2 = sh.xx[it & 1][rt];
-                    scale = x2 > 0.0f ? 1.0f / sqrtf(x2) : 0.0f;
+
+                // score(row, query c):
+                //   cosine     acc / |x|  (queries pre-normalised)       filter bound c
+                //   dot        acc                                        filter bound c |x| |q|
+                //   euclidean  -(|x|^2 + |q|^2 - 2 acc)   (filter only)   filter bound 2c |x| |q|
+                // filter mode buffers the UPPER bound score + bound.
+                const float x2 = sh.xx[it & 1][rt];
+                const float xn = sqrtf(x2);
+                float mul = 1.0f, bnd = 0.0f;
+                if (cosine) mul = x2 > 0.0f ? 1.0f / xn : 0.0f;
+                if (FILTER) {
+                    bnd = cosine ? p.margin_c : bfac * xn;
+                    if (!cosine && row < p.n) atomicMax(&sh.maxxx, __float_as_uint(x2));
+                    if (euclid) mul = 2.0f;
                 }
-                if (row < p.n && !(p.debug & 4)) {
-                    // Compact compare pass -> 64-bit mask of columns worth buffering (NaN passes and is mapped to
-                    // -inf below); the rare pushes run in a small out-of-line loop so the hot code stays a few
-                    // hundred instructions (a fully unrolled push per column was ~40 KB of SASS: I-cache thrash).
+                if (row < p.n) {
+                    // Compact compare pass -> 64-bit mask of columns worth buffering (NaN passes); the rare pushes run
+                    // in a small out-of-line loop so the hot code stays a few hundred instructions (a fully unrolled
+                    // push per column was ~40 KB of SASS: I-cache thrash).
                     uint32_t pass0 = 0, pass1 = 0;
 #pragma unroll
                     for (uint32_t c = 0; c < 32; ++c) {
-                        pass0 |= !(__uint_as_float(v0[c]) * scale < sh.tau[c]) ? (1u << c) : 0u;
-                        pass1 |= !(__uint_as_float(v1[c]) * scale < sh.tau[32 + c]) ? (1u << c) : 0u;
+                        float s0 = __uint_as_float(v0[c]) * mul, s1 = __uint_as_float(v1[c]) * mul;
+                        if (FILTER) {
+                            const float q0n = sh.qn[c], q1n = sh.qn[32 + c];
+                            if (euclid) { s0 -= EUC_KEEP * fmaf(q0n, q0n, x2); s1 -= EUC_KEEP * fmaf(q1n, q1n, x2); }
+                            s0 = fmaf(bnd, q0n, s0);
+                            s1 = fmaf(bnd, q1n, s1);
+                        }
+                        pass0 |= !(s0 < sh.tau[c]) ? (1u << c) : 0u;
+                        pass1 |= !(s1 < sh.tau[32 + c]) ? (1u << c) : 0u;
                     }
                     uint64_t pass = (uint64_t)pass0 | ((uint64_t)pass1 << 32);
                     if (p.nq < 64) pass &= (1ull << p.nq) - 1ull;
@@ -320,48 +373,44 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                             if (c == i) bits = v0[i];
                             if (c == 32 + i) bits = v1[i];
                         }
-                        float sc = __uint_as_float(bits) * scale;
-                        if (sc != sc) sc = -INFINITY;
+                        float sc = __uint_as_float(bits) * mul;
+                        if (FILTER) {
+                            const float qn = sh.qn[c];
+                            if (euclid) sc -= EUC_KEEP * fmaf(qn, qn, x2);
+                            sc = fmaf(bnd, qn, sc);
+                            if (sc != sc) sc = INFINITY;  // undecidable here: keep it, the exact rescoring judges
+                        } else if (sc != sc) {
+                            sc = -INFINITY;
+                        }
                         if (sc >= sh.tau[c]) {
                             int pos = atomicAdd(&sh.cnt[c], 1);
-                            if (pos < p.P) my_cand[(size_t)c * p.P + pos] = make_key(sc, (uint32_t)(p.row_base + row));
+                            if (pos < P) my_cand[(size_t)c * P + pos] = make_key(sc, (uint32_t)(p.row_base + row));
                             else atomicExch(p.flags, 1);
                         }
                     }
                 }
             }
-            // prune any buffer that could overflow during the next tile
+            // prune any buffer that could overflow during the next tile; the 4 epilogue warps prune different
+            // queries concurrently with a register-resident warp selection
             group_sync(EPI_BAR, EPI_THREADS);  // every push of this tile is visible
-            if (p.P == 512) {
-                // register-resident warp selection; the 4 epilogue warps prune different queries concurrently
-                for (uint32_t qi = quad; qi < p.nq; qi += 4)
-                    if (sh.cnt[qi] > prune_at)
-                        warp_prune<16>(my_cand + (size_t)qi * p.P, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr);
-                group_sync(EPI_BAR, EPI_THREADS);
-            } else {
-                uint64_t need = 0;
-                for (uint32_t qi = 0; qi < p.nq; ++qi) need |= (uint64_t)(sh.cnt[qi] > prune_at ? 1 : 0) << qi;
-                group_sync(EPI_BAR, EPI_THREADS);
-                if (need) {
-                    for (uint32_t qi = 0; qi < p.nq; ++qi)
-                        if (need & (1ull << qi))
-                            group_prune(my_cand + (size_t)qi * p.P, p.P, &sh.cnt[qi], &sh.tau[qi], p.k, sbuf, p.P, gtid, EPI_THREADS, EPI_BAR);
-                }
-            }
-        }
-        // emit this CTA's best k per query
-        if (p.P == 512) {
             for (uint32_t qi = quad; qi < p.nq; qi += 4)
-                warp_prune<16>(my_cand + (size_t)qi * p.P, &sh.cnt[qi], &sh.tau[qi], p.k, lane,
-                               p.partial + ((size_t)(p.q0 + qi) * gridDim.x + blockIdx.x) * p.k);
-        } else {
-            for (uint32_t qi = 0; qi < p.nq; ++qi) {
-                group_prune(my_cand + (size_t)qi * p.P, p.P, &sh.cnt[qi], &sh.tau[qi], p.k, sbuf, p.P, gtid, EPI_THREADS, EPI_BAR);
-                uint64_t *dst = p.partial + ((size_t)(p.q0 + qi) * gridDim.x + blockIdx.x) * p.k;
-                for (uint32_t i = gtid; i < p.k; i += EPI_THREADS) dst[i] = sbuf[i];
-                group_sync(EPI_BAR, EPI_THREADS);
-            }
+                if (sh.cnt[qi] > prune_at) {
+                    const float margin2 = !FILTER ? 0.0f : filter_margin2(p.metric, p.margin_c, __uint_as_float(sh.maxxx), sh.qn[qi]);
+                    warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, FILTER, margin2, prune_at);
+                    // everything inside the margin must fit below prune_at, or the next tile could overflow the buffer
+                    if (FILTER && lane == 0 && sh.cnt[qi] >= prune_at) atomicExch(p.flags + 1, 1);
+                }
+            group_sync(EPI_BAR, EPI_THREADS);
         }
+        // emit this CTA's list per query: best k (exact) or everything inside the margin (filter)
+        for (uint32_t qi = quad; qi < p.nq; qi += 4) {
+            const float margin2 = !FILTER ? 0.0f : filter_margin2(p.metric, p.margin_c, __uint_as_float(sh.maxxx), sh.qn[qi]);
+            warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane,
+                           p.partial + ((size_t)(p.q0 + qi) * gridDim.x + blockIdx.x) * p.k_emit, (int)p.k_emit, FILTER, margin2, (int)p.k_emit);
+            // the emitted list was cut at k_emit while rows inside the margin remained -> exact fallback
+            if (FILTER && lane == 0 && sh.cnt[qi] >= (int)p.k_emit && (int)p.k_emit > (int)p.k) atomicExch(p.flags + 1, 1);
+        }
+        if (FILTER && !cosine && tid == EPI_WARP0 * 32) atomicMax(reinterpret_cast<unsigned int *>(p.flags + 2), sh.maxxx);
     }
 
     if (prof && tid == EPI_WARP0 * 32) { g_tc_prof[17] = acc_a; g_tc_prof[18] = clock64() - t_start; g_tc_prof[19] = (long long)num_tiles; }
@@ -369,7 +418,102 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 2) ptx::tmem_dealloc(tmem, TMEM_COLS);
-    if ((p.debug & 64) && tid == 0 && blockIdx.x < 160) g_tc_cta_ns[1][blockIdx.x] = globaltimer_ns();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Exact fp32 re-scoring of the filter survivors (one CTA per query).  cand[q][0..c_out) is sorted by upper bound
+// descending.  Every row whose upper bound reaches (k-th upper bound - 2*Bmax) may belong to the true top-k; they are
+// scored with the same fp32 arithmetic as the CUDA-core scan (dot / sqrt(|x|^2 |q|^2) etc.), sorted by
+// (score desc, row asc) and the best k written out.  If the candidate list is exhausted before the margin ends
+// the overflow flag is raised and the exact tensor-core kernels queued behind redo the search.
+// ---------------------------------------------------------------------------------------------------
+constexpr int RESCORE_THREADS = 256;
+struct RescoreParams {
+    const void *rows;
+    int dtype;
+    uint32_t dim;
+    uint64_t row_base;
+    const float *queries;  // raw fp32 queries [Q x dim]
+    const uint64_t *cand;  // [Q][c_out]
+    uint32_t c_out, k;
+    int metric;
+    float margin_c;
+    int *flags;
+    uint64_t *out;         // [Q][k]
+};
+
+__global__ void __launch_bounds__(RESCORE_THREADS) rescore_kernel(RescoreParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *sbuf = reinterpret_cast<uint64_t *>(smem_raw);           // 1024 keys
+    float *qs = reinterpret_cast<float *>(smem_raw + 1024 * 8);        // query
+    __shared__ float s_qq;
+    __shared__ int s_count;
+    const uint32_t q = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t *cand = p.cand + (size_t)q * p.c_out;
+    for (uint32_t j = tid; j < p.dim; j += RESCORE_THREADS) qs[j] = p.queries[(size_t)q * p.dim + j];
+    if (tid == 0) s_count = (int)p.c_out;
+    __syncthreads();
+    if (warp == 0) {
+        float a = 0.0f;
+        for (uint32_t j = lane; j < p.dim; j += 32) a = fmaf(qs[j], qs[j], a);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) s_qq = a;
+    }
+    __syncthreads();
+    // margin: 2 * c * max|x| * |q|  (cosine: 2c; euclidean bound is on -dist^2: 2 * 2c|x||q|)
+    const float margin2 = filter_margin2(p.metric, p.margin_c, __uint_as_float((unsigned int)p.flags[2]), sqrtf(s_qq));
+    const uint64_t kth_key = p.k <= p.c_out ? cand[p.k - 1] : 0ull;
+    const float thr = kth_key ? key_score(kth_key) - margin2 : -INFINITY;
+    for (uint32_t i = tid; i < p.c_out; i += RESCORE_THREADS) {
+        uint64_t key = cand[i];
+        if (key == 0ull || key_score(key) < thr) atomicMin(&s_count, (int)i);
+    }
+    __syncthreads();
+    const int count = s_count;
+    if (count == (int)p.c_out && tid == 0) atomicExch(p.flags + 1, 1);  // list exhausted while still inside the margin
+    // exact scores
+    for (int i = warp; i < count; i += RESCORE_THREADS / 32) {
+        const uint32_t grow = key_row(cand[i]);
+        const size_t local = (size_t)(grow - (uint32_t)p.row_base);
+        float d = 0.0f, xx = 0.0f;
+        if (p.dtype == NK_DTYPE_F16) {
+            const __half *x = static_cast<const __half *>(p.rows) + local * p.dim;
+            for (uint32_t j = lane; j < p.dim; j += 32) {
+                float v = __half2float(x[j]);
+                if (p.metric == NK_METRIC_EUCLIDEAN) { float t = v - qs[j]; d = fmaf(t, t, d); }
+                else { d = fmaf(v, qs[j], d); xx = fmaf(v, v, xx); }
+            }
+        } else {
+            const float *x = static_cast<const float *>(p.rows) + local * p.dim;
+            for (uint32_t j = lane; j < p.dim; j += 32) {
+                float v = __ldg(x + j);
+                if (p.metric == NK_METRIC_EUCLIDEAN) { float t = v - qs[j]; d = fmaf(t, t, d); }
+                else { d = fmaf(v, qs[j], d); xx = fmaf(v, v, xx); }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            d += __shfl_xor_sync(0xffffffffu, d, o);
+            xx += __shfl_xor_sync(0xffffffffu, xx, o);
+        }
+        if (lane == 0) {
+            float s = d;
+            if (p.metric == NK_METRIC_EUCLIDEAN) s = -d;
+            else if (p.metric == NK_METRIC_COSINE) {
+                float den = sqrtf(xx * s_qq);
+                s = den > 0.0f ? d / den : 0.0f;
+            }
+            if (s != s) s = -INFINITY;
+            sbuf[i] = make_key(s, grow);
+        }
+    }
+    int P2 = 32;
+    while (P2 < count) P2 <<= 1;
+    for (int i = count + tid; i < P2; i += RESCORE_THREADS) sbuf[i] = 0ull;
+    block_bitonic_sort_desc(sbuf, P2);
+    for (uint32_t i = tid; i < p.k; i += RESCORE_THREADS) p.out[(size_t)q * p.k + i] = (int)i < count ? sbuf[i] : 0ull;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -411,92 +555,162 @@ static int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint32_t di
     return 0;
 }
 
-bool scan_tensor_supported(const DeviceInfo &di, const ScanArgs &a) {
+static bool tc_common_ok(const DeviceInfo &di, const ScanArgs &a) {
     if (di.cc < 100) return false;
-    if (a.dtype != NK_DTYPE_F32) return false;                      // fp16 corpus: CUDA-core scan (HBM-bound at Q=1)
-    if (a.metric == NK_METRIC_EUCLIDEAN) return false;              // needs exact rescoring of |x|^2+|q|^2-2xq; SIMT path
+    if (a.dtype != NK_DTYPE_F32) return false;                      // fp16 corpus: CUDA-core scan (HBM-bound at small Q)
     if (a.dim % 4 != 0 || a.dim < 32) return false;                 // TMA: 16-byte global stride
     if ((reinterpret_cast<uintptr_t>(a.rows) & 15) != 0) return false;
-    if (a.k > NK_MAX_K || a.n == 0) return false;
-    if (next_pow2(a.k + tc::ROWS + 1) > 1024) return false;          // sort buffer must fit beside the rings (k <= 767)
+    if (a.n == 0 || a.k == 0) return false;
     return true;
+}
+// exact (3xTF32) mode: cosine / dot, k <= 255 (register-resident prune over a 512-slot buffer)
+bool scan_tensor_supported(const DeviceInfo &di, const ScanArgs &a) {
+    return tc_common_ok(di, a) && a.metric != NK_METRIC_EUCLIDEAN && a.k + tc::ROWS + 1 <= (uint32_t)tc::P;
+}
+// filter (1xTF32 + exact rescoring) mode: all three metrics, k <= 192
+bool scan_tensor_filter_supported(const DeviceInfo &di, const ScanArgs &a) {
+    return tc_common_ok(di, a) && a.k <= 192;
+}
+
+static int tc_debug_flags() {
+    const char *dbg = getenv("NK_TC_DEBUG");
+    return dbg ? atoi(dbg) : 0;
+}
+
+template <int NT>
+static int launch_passes(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint32_t grid, uint32_t k_emit, float margin_c,
+                         const float *qhi, const float *qlo, const float *qnorm, uint32_t Qpad, const int *only_if,
+                         uint64_t *launches, bool count_main) {
+    using namespace tc;
+    CUtensorMap map_rows, map_qhi, map_qlo;
+    if (make_map(&map_rows, a.rows, a.n, a.dim, ROWS)) return -1;
+    if (make_map(&map_qhi, qhi, Qpad, a.dim, QT)) return -1;
+    if (make_map(&map_qlo, qlo ? qlo : qhi, Qpad, a.dim, QT)) return -1;
+    const size_t smem = (size_t)Cfg<NT>::RING_BYTES + sizeof(Shared) + 1024;
+    if (smem > di.max_smem_optin) {
+        set_error("tensor path needs %zu B shared memory (> %zu)", smem, di.max_smem_optin);
+        return -1;
+    }
+    NK_CUDA_OK(cudaFuncSetAttribute(knn_scan_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (uint32_t q0 = 0; q0 < a.Q; q0 += QT) {
+        Params p;
+        p.n = a.n; p.dim = a.dim; p.nslab = (a.dim + BK - 1) / BK; p.row_base = a.row_base;
+        p.q0 = q0; p.nq = a.Q - q0 < (uint32_t)QT ? a.Q - q0 : (uint32_t)QT; p.k = a.k;
+        p.metric = a.metric; p.k_emit = k_emit; p.margin_c = margin_c; p.qnorm = qnorm;
+        p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = only_if; p.debug = tc_debug_flags();
+        knn_scan_tc_kernel<NT><<<grid, THREADS, smem, a.stream>>>(map_rows, map_qhi, map_qlo, p);
+        NK_CUDA_OK(cudaGetLastError());
+        if (launches) ++*launches;
+        if (count_main && a.main_launches) ++*a.main_launches;
+    }
+    return 0;
+}
+
+static void tc_print_prof(cudaStream_t stream, uint32_t num_tiles, uint32_t grid, uint32_t nslab) {
+    if (!(tc_debug_flags() & 64)) return;
+    long long h[32];
+    cudaStreamSynchronize(stream);
+    cudaMemcpyFromSymbol(h, g_tc_prof, sizeof(h));
+    uint32_t slabs = ((num_tiles + grid - 1) / grid) * nslab;
+    fprintf(stderr, "[tc prof CTA0, ~%u slabs] total %lld cyc (%.0f/slab)\n  tmaA wait aempty_s %lld | tmaB wait bempty %lld\n"
+            "  mma: wait bfull %lld, wait accempty %lld, wait afull %lld, total %lld\n"
+            "  split m0: wait afull_s %lld, wait aempty %lld, read+math %lld, st+arrive %lld, total %lld\n"
+            "  split m1: wait afull_s %lld, wait aempty %lld, read+math %lld, st+arrive %lld\n  epi: wait accfull %lld total %lld\n",
+            slabs, h[7], (double)h[7] / slabs, h[0], h[2], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15], h[16], h[17], h[18]);
+}
+
+// Exact 3xTF32 scan.  only_if != nullptr: every kernel early-exits unless *only_if != 0 (device-side fallback).
+static int scan_tensor_exact(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *out_keys, uint64_t *launches,
+                             const int *only_if, bool prep, bool count_main) {
+    using namespace tc;
+    const uint32_t Qpad = (a.Q + QT - 1) / QT * QT;
+    const uint32_t num_tiles = (a.n + ROWS - 1) / ROWS;
+    uint32_t grid = (uint32_t)di.num_sms;
+    if (grid > num_tiles) grid = num_tiles;
+    if (ws_reserve((void **)&ws.qaux, &ws.qaux_bytes, ((size_t)2 * Qpad * a.dim + Qpad) * 4)) return -1;
+    if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)grid * QT * P * 8)) return -1;
+    if (ws_reserve((void **)&ws.partial, &ws.partial_bytes, (size_t)a.Q * grid * a.k * 8)) return -1;
+    float *qhi = ws.qaux, *qlo = ws.qaux + (size_t)Qpad * a.dim, *qnorm = ws.qaux + (size_t)2 * Qpad * a.dim;
+    if (prep) {
+        tc_prep_queries_kernel<<<Qpad, 256, 0, a.stream>>>(a.queries, a.Q, a.dim, a.metric == NK_METRIC_COSINE, qhi, qlo, qnorm);
+        NK_CUDA_OK(cudaGetLastError());
+        if (launches) ++*launches;
+    }
+    if (count_main && a.ev_begin) NK_CUDA_OK(cudaEventRecord(a.ev_begin, a.stream));
+    if (launch_passes<3>(di, a, ws, grid, a.k, 0.0f, qhi, qlo, nullptr, Qpad, only_if, launches, count_main)) return -1;
+    if (count_main && a.ev_end) NK_CUDA_OK(cudaEventRecord(a.ev_end, a.stream));
+    if (merge_keys(ws.partial, grid, a.k, (size_t)grid * a.k, a.Q, a.k, out_keys, a.stream, only_if)) return -1;
+    if (launches) ++*launches;
+    if (count_main) tc_print_prof(a.stream, num_tiles, grid, (a.dim + BK - 1) / BK);
+    return 0;
 }
 
 int scan_tensor(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *out_keys, uint64_t *launches) {
-    using namespace tc;
     if (a.n == 0 || a.Q == 0 || a.k == 0) return 0;
     if (!scan_tensor_supported(di, a)) {
         set_error("tensor path: unsupported shape");
         return -1;
     }
+    return scan_tensor_exact(di, a, ws, out_keys, launches, nullptr, true, true);
+}
+
+// Filter mode: 1xTF32 scan with rigorous margins -> merge by upper bound -> exact fp32 rescoring; the exact 3xTF32
+// search is enqueued behind it and runs only if the device-side overflow flag was raised.
+int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *out_keys, uint64_t *launches) {
+    using namespace tc;
+    if (a.n == 0 || a.Q == 0 || a.k == 0) return 0;
+    if (!scan_tensor_filter_supported(di, a)) {
+        set_error("tensor filter path: unsupported shape");
+        return -1;
+    }
     const uint32_t Qpad = (a.Q + QT - 1) / QT * QT;
-    const uint32_t nslab = (a.dim + BK - 1) / BK;
-    const uint32_t P = next_pow2(a.k + ROWS + 1) < 512 ? 512 : next_pow2(a.k + ROWS + 1);
     const uint32_t num_tiles = (a.n + ROWS - 1) / ROWS;
     uint32_t grid = (uint32_t)di.num_sms;
     if (grid > num_tiles) grid = num_tiles;
+    // per-CTA list: k + room for the rows inside the margin; merged candidate list per query
+    uint32_t k_emit = next_pow2(a.k + a.k / 2 + 32);
+    if (k_emit < 64) k_emit = 64;
+    if (k_emit > (uint32_t)(P - ROWS)) k_emit = P - ROWS;
+    uint32_t c_out = next_pow2(2 * a.k + 64);
+    if (c_out < 128) c_out = 128;
+    if (c_out > 1024) c_out = 1024;
+    // 2^-10 (tf32 rounding of both operands) + d * 2^-22 (fp32 accumulation, truncating adders) + fp32 rounding of the norms
+    const float margin_c = 9.765625e-4f + (float)a.dim * 2.384185791015625e-7f + 4e-6f;
 
-    if (ws_reserve((void **)&ws.qaux, &ws.qaux_bytes, (size_t)2 * Qpad * a.dim * 4)) return -1;
+    if (ws_reserve((void **)&ws.qaux, &ws.qaux_bytes, ((size_t)2 * Qpad * a.dim + Qpad) * 4)) return -1;
     if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)grid * QT * P * 8)) return -1;
-    if (ws_reserve((void **)&ws.partial, &ws.partial_bytes, (size_t)a.Q * grid * a.k * 8)) return -1;
-    float *qhi = ws.qaux, *qlo = ws.qaux + (size_t)Qpad * a.dim;
+    if (ws_reserve((void **)&ws.partial, &ws.partial_bytes, (size_t)a.Q * grid * k_emit * 8)) return -1;
+    if (ws_reserve((void **)&ws.keys2, &ws.keys2_bytes, (size_t)a.Q * c_out * 8)) return -1;
+    float *qhi = ws.qaux, *qlo = ws.qaux + (size_t)Qpad * a.dim, *qnorm = ws.qaux + (size_t)2 * Qpad * a.dim;
 
-    tc_prep_queries_kernel<<<Qpad, 256, 0, a.stream>>>(a.queries, a.Q, Qpad, a.dim, a.metric == NK_METRIC_COSINE, qhi, qlo);
+    NK_CUDA_OK(cudaMemsetAsync(ws.flags + 1, 0, 2 * sizeof(int), a.stream));  // [1] overflow, [2] max |x|^2
+    const bool can_fallback = scan_tensor_supported(di, a);  // euclidean has no 3xTF32 twin: overflow -> error
+    tc_prep_queries_kernel<<<Qpad, 256, 0, a.stream>>>(a.queries, a.Q, a.dim, a.metric == NK_METRIC_COSINE, qhi,
+                                                       can_fallback ? qlo : nullptr, qnorm);
     NK_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
-
-    CUtensorMap map_rows, map_qhi, map_qlo;
-    if (make_map(&map_rows, a.rows, a.n, a.dim, ROWS)) return -1;
-    if (make_map(&map_qhi, qhi, Qpad, a.dim, QT)) return -1;
-    if (make_map(&map_qlo, qlo, Qpad, a.dim, QT)) return -1;
-
-    const size_t smem = (size_t)RING_BYTES + (size_t)P * 8 + sizeof(Shared) + 1024;
-    if (smem > di.max_smem_optin) {
-        set_error("tensor path needs %zu B shared memory (> %zu)", smem, di.max_smem_optin);
-        return -1;
-    }
-    NK_CUDA_OK(cudaFuncSetAttribute(knn_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-
     if (a.ev_begin) NK_CUDA_OK(cudaEventRecord(a.ev_begin, a.stream));
-    for (uint32_t q0 = 0; q0 < a.Q; q0 += QT) {
-        Params p;
-        p.n = a.n; p.dim = a.dim; p.nslab = nslab; p.row_base = a.row_base;
-        p.q0 = q0; p.nq = a.Q - q0 < (uint32_t)QT ? a.Q - q0 : (uint32_t)QT; p.k = a.k;
-        p.metric = a.metric; p.P = (int)P; p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags;
-        {
-            const char *dbg = getenv("NK_TC_DEBUG");
-            p.debug = dbg ? atoi(dbg) : 0;
-        }
-        knn_scan_tc_kernel<<<grid, THREADS, smem, a.stream>>>(map_rows, map_qhi, map_qlo, p);
-        NK_CUDA_OK(cudaGetLastError());
-        if (launches) ++*launches;
-        if (a.main_launches) ++*a.main_launches;
-    }
+    if (launch_passes<1>(di, a, ws, grid, k_emit, margin_c, qhi, nullptr, qnorm, Qpad, nullptr, launches, true)) return -1;
     if (a.ev_end) NK_CUDA_OK(cudaEventRecord(a.ev_end, a.stream));
-    if (merge_keys(ws.partial, grid, a.k, (size_t)grid * a.k, a.Q, a.k, out_keys, a.stream)) return -1;
-    if (launches) ++*launches;
-    {
-        const char *dbg = getenv("NK_TC_DEBUG");
-        if (dbg && (atoi(dbg) & 64)) {
-            long long h[32];
-            cudaStreamSynchronize(a.stream);
-            cudaMemcpyFromSymbol(h, g_tc_prof, sizeof(h));
-            uint32_t slabs = ((num_tiles + grid - 1) / grid) * nslab;
-            {
-                unsigned long long c[2][160];
-                cudaMemcpyFromSymbol(c, g_tc_cta_ns, sizeof(c));
-                unsigned long long t0 = ~0ull;
-                for (uint32_t i = 0; i < grid && i < 160; ++i) t0 = c[0][i] < t0 ? c[0][i] : t0;
-                fprintf(stderr, "[tc per-CTA end times, us since first start]");
-                for (uint32_t i = 0; i < grid && i < 160; ++i) fprintf(stderr, "%s%.0f", i % 16 ? " " : "\n  ", (double)(c[1][i] - t0) / 1e3);
-                fprintf(stderr, "\n");
-            }
-            fprintf(stderr, "[tc prof CTA0, ~%u slabs] total %lld cyc (%.0f/slab)\n  tmaA wait aempty_s %lld | tmaB wait bempty %lld\n"
-                    "  mma: wait bfull %lld, wait accempty %lld, wait afull %lld, total %lld\n"
-                    "  split m0: wait afull_s %lld, wait aempty %lld, read+math %lld, st+arrive %lld, total %lld\n"
-                    "  split m1: wait afull_s %lld, wait aempty %lld, read+math %lld, st+arrive %lld\n  epi: wait accfull %lld total %lld\n",
-                    slabs, h[7], (double)h[7] / slabs, h[0], h[2], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15], h[16], h[17], h[18]);
-        }
+    if (merge_keys(ws.partial, grid, k_emit, (size_t)grid * k_emit, a.Q, c_out, ws.keys2, a.stream, nullptr, k_emit)) return -1;
+    RescoreParams rp;
+    rp.rows = a.rows; rp.dtype = a.dtype; rp.dim = a.dim; rp.row_base = a.row_base; rp.queries = a.queries;
+    rp.cand = ws.keys2; rp.c_out = c_out; rp.k = a.k; rp.metric = a.metric; rp.margin_c = margin_c; rp.flags = ws.flags; rp.out = out_keys;
+    const size_t rsmem = 1024 * 8 + (size_t)a.dim * 4;
+    NK_CUDA_OK(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
+    rescore_kernel<<<a.Q, RESCORE_THREADS, rsmem, a.stream>>>(rp);
+    NK_CUDA_OK(cudaGetLastError());
+    if (launches) *launches += 2;
+    tc_print_prof(a.stream, num_tiles, grid, (a.dim + BK - 1) / BK);
+    // queued behind; every kernel returns at once unless flags[1] was raised on the device
+    if (can_fallback) {
+        if (scan_tensor_exact(di, a, ws, out_keys, launches, ws.flags + 1, false, false)) return -1;
+    } else {
+        ScanArgs b = a;  // euclidean / large k: the CUDA-core scan is the exact twin
+        b.only_if = ws.flags + 1;
+        b.ev_begin = b.ev_end = nullptr;
+        b.main_launches = nullptr;
+        if (scan_simt(di, b, ws, out_keys, launches)) return -1;
     }
     return 0;
 }

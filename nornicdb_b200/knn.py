@@ -14,7 +14,7 @@ from . import _lib
 
 METRICS = {"cosine": 0, "dot": 1, "euclidean": 2}
 DTYPES = {"f32": 0, "fp32": 0, "float32": 0, "f16": 1, "fp16": 1, "float16": 1}
-PATHS = {"auto": 0, "simt": 1, "tensor": 2}
+PATHS = {"auto": 0, "simt": 1, "tensor": 2, "filter": 3}
 NK_MAX_K = 1024
 
 
@@ -98,8 +98,13 @@ class KnnIndex:
                "nk_index_read_rows")
         return out
 
+    def debug_flags(self):
+        out = (C.c_int * 4)()
+        _check(self.lib.nk_index_debug_flags(self.ptr, out), "nk_index_debug_flags")
+        return [int(v) for v in out]
+
     def last_path(self) -> str:
-        return {1: "simt", 2: "tensor"}.get(int(self.lib.nk_index_last_path(self.ptr)), "?")
+        return {1: "simt", 2: "tensor", 3: "filter"}.get(int(self.lib.nk_index_last_path(self.ptr)), "?")
 
     def enable_timing(self, on: bool = True) -> None:
         _check(self.lib.nk_index_enable_timing(self.ptr, 1 if on else 0), "nk_index_enable_timing")
