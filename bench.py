@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
     ap.add_argument("--path", default="auto", choices=["auto", "simt", "tensor", "filter"])
     ap.add_argument("--rows", type=int, default=0, help="override N_total (debug)")
+    ap.add_argument("--k", type=int, default=0, help="override k (debug)")
+    ap.add_argument("--q", type=int, default=0, help="override Q (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -197,6 +199,12 @@ def main():
     N_total, dim, dtype, Q, k, metric, desc = WORKLOADS[args.workload]
     if args.rows:
         N_total = args.rows
+    if args.k:
+        k = args.k
+    if args.q:
+        Q = args.q
+    if args.rows or args.k or args.q:
+        desc += f" [debug override: N={N_total} Q={Q} k={k}]"
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -179,50 +179,77 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
     }
     return v;
 }
-// margin_mode (tensor-core filter scan): keys carry UPPER bounds; after the k-th best everything whose bound is
-// still >= (k-th bound - margin2) is kept as well (it may beat the k-th once re-scored exactly), up to max_keep
-// entries, and tau = k-th bound - margin2.  Exact mode keeps exactly the best k and tau = k-th score.
+// Warp-level prune by RADIX SELECT (cost independent of k): the buffered keys sit in registers (PER_LANE per lane);
+// the k-th largest key is found by a most-significant-bit-first binary search whose population counts are one
+// redux.sync each, then the survivors are compacted back (unsorted - merge_keys sorts).
+//   exact mode : keeps exactly the k largest keys (64-bit search: score, then lowest row);  tau = k-th score.
+//   margin mode (tensor-core filter scan; keys carry UPPER bounds): 32-bit search for the k-th largest bound S_k,
+//                then keeps everything with bound >= S_k - margin2 (it may beat the k-th once re-scored exactly), at
+//                most max_keep entries;  tau = S_k - margin2.
+// Caller guarantees every producer of cand[] has finished (barrier) and that *cnt <= 32*PER_LANE.
 template <int PER_LANE>
 __device__ __forceinline__ void warp_prune(uint64_t *cand, int *cnt, float *tau, uint32_t k, int lane, uint64_t *out,
                                            int out_len, bool margin_mode, float margin2, int max_keep) {
     int n = *cnt;
     if (n > 32 * PER_LANE) n = 32 * PER_LANE;
     uint64_t v[PER_LANE];
-    uint64_t lmax = 0;
 #pragma unroll
     for (int i = 0; i < PER_LANE; ++i) {
         int idx = lane + 32 * i;
         v[i] = idx < n ? cand[idx] : 0ull;
-        lmax = v[i] > lmax ? v[i] : lmax;
     }
     __syncwarp();
-    const int limit = margin_mode ? (n < max_keep ? n : max_keep) : (n < (int)k ? n : (int)k);
-    float kth = -INFINITY;
-    int keep = 0;
-    for (int j = 0; j < limit; ++j) {
-        const uint64_t m = warp_max_u64(lmax);
-        if (m == 0ull) break;
-        if (j >= (int)k && key_score(m) < kth - margin2) break;  // margin mode only (exact mode stops at limit == k)
-        if (j == (int)k - 1) kth = key_score(m);
-        keep = j + 1;
-        if (lane == 0) {
-            cand[j] = m;
-            if (out && j < out_len) out[j] = m;
-        }
-        if (lmax == m) {  // keys are unique (row id in the low word): exactly one lane owns it
-            lmax = 0;
+    uint64_t thr_key = 1ull;  // keep every live key
+    float new_tau = -INFINITY;
+    if (n >= (int)k) {
+        uint64_t prefix = 0ull;
+        const int low = margin_mode ? 32 : 0;
+#pragma unroll 1
+        for (int bit = 63; bit >= low; --bit) {
+            const uint64_t c = prefix | (1ull << bit);
+            int mine = 0;
 #pragma unroll
-            for (int i = 0; i < PER_LANE; ++i) {
-                if (v[i] == m) v[i] = 0ull;
-                lmax = v[i] > lmax ? v[i] : lmax;
+            for (int i = 0; i < PER_LANE; ++i) mine += v[i] >= c ? 1 : 0;
+            if (__reduce_add_sync(0xffffffffu, mine) >= (int)k) prefix = c;
+        }
+        if (margin_mode) {
+            new_tau = ord_to_float((uint32_t)(prefix >> 32)) - margin2;
+            thr_key = (uint64_t)ord_bits(new_tau) << 32;  // lowest key with that score
+            if (thr_key == 0ull) thr_key = 1ull;
+        } else {
+            new_tau = key_score(prefix);
+            thr_key = prefix;
+        }
+    }
+    // compaction: exclusive prefix of per-lane survivor counts
+    int mine = 0;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) mine += v[i] >= thr_key ? 1 : 0;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int cap = margin_mode ? max_keep : (int)k;
+    const int keep = total < cap ? total : cap;
+    int pos = incl - mine;
+#pragma unroll
+    for (int i = 0; i < PER_LANE; ++i) {
+        if (v[i] >= thr_key) {
+            if (pos < keep) {
+                cand[pos] = v[i];
+                if (out && pos < out_len) out[pos] = v[i];
             }
+            ++pos;
         }
     }
     if (out)
         for (int j = keep + lane; j < out_len; j += 32) out[j] = 0ull;
     if (lane == 0) {
         *cnt = keep;
-        *tau = (n >= (int)k) ? kth - (margin_mode ? margin2 : 0.0f) : -INFINITY;
+        *tau = new_tau;
     }
     __syncwarp();
 }
