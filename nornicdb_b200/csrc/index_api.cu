@@ -133,7 +133,7 @@ static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uin
         }
     }
     ix->last_path = use;
-    if (rc == 0) ix->stats.bytes_scanned += (uint64_t)s.n * ix->dim * ix->esz() * (use_tensor ? ((Q + 63) / 64) : ((Q + 7) / 8));
+    if (rc == 0) ix->stats.bytes_scanned += (uint64_t)s.n * ix->dim * ix->esz() * (use == NK_PATH_TENSOR_FILTER ? ((Q + 127) / 128) : use_tensor ? ((Q + 63) / 64) : ((Q + 7) / 8));
     return rc;
 }
 

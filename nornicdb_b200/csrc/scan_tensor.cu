@@ -42,14 +42,12 @@ namespace nk {
 namespace tc {
 constexpr int THREADS = 512;
 constexpr int ROWS = 256;        // corpus rows per tile (2 M-tiles of 128)
-constexpr int QT = 64;           // queries per launch (MMA N)
+constexpr int QT_MAX = 128;      // queries per launch (MMA N): 64, or 128 for large batches (filter mode)
 constexpr int BK = 32;           // floats per K-slab = one 128-byte swizzle row
 constexpr int ASTAGES = 4;       // corpus-slab smem ring
 constexpr int A_BYTES = ROWS * BK * 4;   // 32 KB
-constexpr int B_BYTES = QT * BK * 4;     // 8 KB per part
 constexpr int TMEM_COLS = 512;
-constexpr int ACC_COL = 0;       // [mtile] x 64 columns (single-buffered, drained per M-tile)
-constexpr int A_COL = 128;       // TMEM A-operand ring: 384 columns
+constexpr int ACC_COL = 0;       // [mtile] x QT columns (single-buffered, drained per M-tile); the A ring follows
 constexpr int EPI_THREADS = 128;
 constexpr int EPI_BAR = 1;
 constexpr int SPLIT_WARP0 = 4, EPI_WARP0 = 12;
@@ -58,12 +56,15 @@ constexpr int P = 512;           // candidate buffer capacity per (CTA, query): 
 constexpr float EUC_EPS = 4e-6f;  // fp32 rounding of |x|^2 + |q|^2 in the euclidean upper bound
 constexpr float EUC_KEEP = 1.0f - EUC_EPS;
 
-template <int NT> struct Cfg {
+template <int NT, int QT> struct Cfg {
     static constexpr int PARTS = NT == 3 ? 2 : 1;          // hi (+ lo)
+    static constexpr int B_BYTES = QT * BK * 4;            // one part of one query slab (8 / 16 KB)
     static constexpr int BST_BYTES = PARTS * B_BYTES;
-    static constexpr int BSTAGES = NT == 3 ? 5 : 8;        // 80 KB / 64 KB
-    static constexpr int TSTAGES = NT == 3 ? 3 : 6;        // 128 / 64 TMEM columns per stage
+    static constexpr int BSTAGES = (80 * 1024) / BST_BYTES > MAX_BSTAGES ? MAX_BSTAGES : (80 * 1024) / BST_BYTES;
+    static constexpr int A_COL = 2 * QT;                   // TMEM: accumulators [2][QT], then the A-operand ring
+    static constexpr int TSTAGES = (TMEM_COLS - A_COL) / (2 * PARTS * BK);  // 3 / 6 (QT=64), 4 (QT=128 filter)
     static constexpr int RING_BYTES = ASTAGES * A_BYTES + BSTAGES * BST_BYTES;
+    static_assert(BSTAGES >= 2 && TSTAGES >= 2 && TSTAGES <= MAX_TSTAGES, "ring too shallow");
 };
 
 struct Params {
@@ -75,6 +76,7 @@ struct Params {
     float margin_c;           // filter mode: c in |s_hat - s| <= c |x| |q|
     const float *qnorm;       // filter mode: |q| per query (1 for cosine), padded to a multiple of 64
     uint64_t *cand;           // [grid][QT][P]
+    uint32_t qpad_off;        // row of this launch's first query inside the padded hi/lo/qnorm arrays
     uint64_t *partial;        // [Q][grid][k_emit]
     int *flags;               // [0] fatal buffer overflow, [1] filter-margin overflow (-> exact fallback), [2] max |x|^2 bits
     const int *only_if;       // exact fallback: run only if *only_if != 0
@@ -89,9 +91,9 @@ struct __align__(8) Shared {
     uint32_t tmem_base;
     unsigned int maxxx;       // running max of |x|^2 (float bits) over the rows this CTA has scored
     float xx[2][ROWS];
-    float tau[QT];
-    float qn[QT];
-    int cnt[QT];
+    float tau[QT_MAX];
+    float qn[QT_MAX];
+    int cnt[QT_MAX];
 };
 }  // namespace tc
 
@@ -136,13 +138,14 @@ __global__ void tc_prep_queries_kernel(const float *q, uint32_t Q, uint32_t dim,
     }
 }
 
-template <int NT>
+template <int NT, int QT>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_qhi,
                    const __grid_constant__ CUtensorMap map_qlo, tc::Params p) {
     using namespace tc;
-    using C = Cfg<NT>;
+    using C = Cfg<NT, QT>;
     constexpr bool FILTER = NT == 1;
+    constexpr int A_COL = C::A_COL, B_BYTES = C::B_BYTES;
     if (p.only_if && *p.only_if == 0) return;  // exact fallback not needed (uniform over the grid)
 
     extern __shared__ unsigned char smem_dyn[];
@@ -175,7 +178,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
     if (tid < QT) {
         sh.tau[tid] = -INFINITY;
         sh.cnt[tid] = 0;
-        sh.qn[tid] = (FILTER && p.qnorm) ? p.qnorm[p.q0 + tid] : 1.0f;
+        sh.qn[tid] = (FILTER && p.qnorm) ? p.qnorm[p.qpad_off + tid] : 1.0f;
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -207,8 +210,8 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                 if (ptx::elect_one_sync()) {
                     unsigned char *st = b_base + (size_t)s * C::BST_BYTES;
                     ptx::mbar_arrive_expect_tx(&sh.bfull[s], C::BST_BYTES);
-                    ptx::tma_load_2d(&map_qhi, &sh.bfull[s], st, (int32_t)(j * BK), (int32_t)p.q0, ptx::CACHE_EVICT_LAST);
-                    if (NT == 3) ptx::tma_load_2d(&map_qlo, &sh.bfull[s], st + B_BYTES, (int32_t)(j * BK), (int32_t)p.q0, ptx::CACHE_EVICT_LAST);
+                    ptx::tma_load_2d(&map_qhi, &sh.bfull[s], st, (int32_t)(j * BK), (int32_t)p.qpad_off, ptx::CACHE_EVICT_LAST);
+                    if (NT == 3) ptx::tma_load_2d(&map_qlo, &sh.bfull[s], st + B_BYTES, (int32_t)(j * BK), (int32_t)p.qpad_off, ptx::CACHE_EVICT_LAST);
                 }
                 __syncwarp();
             }
@@ -321,15 +324,6 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                 const uint32_t row = tile * ROWS + rt;
                 { TC_PROF_BEGIN(); ptx::mbar_wait(&sh.accfull[m], it & 1); TC_PROF_END(a); }
                 ptx::tc_fence_after();
-                // drain the accumulator first and hand it back, then score from registers
-                uint32_t v0[32], v1[32];
-                ptx::tmem_ld_32x32b_x32(tmem + lane_base + ACC_COL + m * QT, v0);
-                ptx::tmem_ld_32x32b_x32(tmem + lane_base + ACC_COL + m * QT + 32, v1);
-                ptx::tmem_wait_ld();
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&sh.accempty[m]);
-
                 // score(row, query c):
                 //   cosine     acc / |x|  (queries pre-normalised)       filter bound c
                 //   dot        acc                                        filter bound c |x| |q|
@@ -344,48 +338,64 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                     if (!cosine && row < p.n) atomicMax(&sh.maxxx, __float_as_uint(x2));
                     if (euclid) mul = 2.0f;
                 }
-                if (row < p.n) {
-                    // Compact compare pass -> 64-bit mask of columns worth buffering (NaN passes); the rare pushes run
-                    // in a small out-of-line loop so the hot code stays a few hundred instructions (a fully unrolled
-                    // push per column was ~40 KB of SASS: I-cache thrash).
-                    uint32_t pass0 = 0, pass1 = 0;
-#pragma unroll
-                    for (uint32_t c = 0; c < 32; ++c) {
-                        float s0 = __uint_as_float(v0[c]) * mul, s1 = __uint_as_float(v1[c]) * mul;
-                        if (FILTER) {
-                            const float q0n = sh.qn[c], q1n = sh.qn[32 + c];
-                            if (euclid) { s0 -= EUC_KEEP * fmaf(q0n, q0n, x2); s1 -= EUC_KEEP * fmaf(q1n, q1n, x2); }
-                            s0 = fmaf(bnd, q0n, s0);
-                            s1 = fmaf(bnd, q1n, s1);
-                        }
-                        pass0 |= !(s0 < sh.tau[c]) ? (1u << c) : 0u;
-                        pass1 |= !(s1 < sh.tau[32 + c]) ? (1u << c) : 0u;
-                    }
-                    uint64_t pass = (uint64_t)pass0 | ((uint64_t)pass1 << 32);
-                    if (p.nq < 64) pass &= (1ull << p.nq) - 1ull;
 #pragma unroll 1
-                    while (pass) {
-                        const uint32_t c = (uint32_t)__ffsll((long long)pass) - 1u;
-                        pass &= pass - 1ull;
-                        uint32_t bits = 0;
+                for (uint32_t half = 0; half < QT / 64; ++half) {
+                    // drain 64 accumulator columns into registers; after the last half hand the accumulator back,
+                    // then score from registers
+                    const uint32_t cb = half * 64;
+                    uint32_t v0[32], v1[32];
+                    ptx::tmem_ld_32x32b_x32(tmem + lane_base + ACC_COL + m * QT + cb, v0);
+                    ptx::tmem_ld_32x32b_x32(tmem + lane_base + ACC_COL + m * QT + cb + 32, v1);
+                    ptx::tmem_wait_ld();
+                    if (half + 1 == QT / 64) {
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(&sh.accempty[m]);
+                    }
+                    if (row < p.n && cb < p.nq) {
+                        // Compact compare pass -> 64-bit mask of columns worth buffering (NaN passes); the rare pushes
+                        // run in a small out-of-line loop so the hot code stays a few hundred instructions (a fully
+                        // unrolled push per column was ~40 KB of SASS: I-cache thrash).
+                        uint32_t pass0 = 0, pass1 = 0;
 #pragma unroll
-                        for (uint32_t i = 0; i < 32; ++i) {  // register file is not indexable: select by compare
-                            if (c == i) bits = v0[i];
-                            if (c == 32 + i) bits = v1[i];
+                        for (uint32_t c = 0; c < 32; ++c) {
+                            float s0 = __uint_as_float(v0[c]) * mul, s1 = __uint_as_float(v1[c]) * mul;
+                            if (FILTER) {
+                                const float q0n = sh.qn[cb + c], q1n = sh.qn[cb + 32 + c];
+                                if (euclid) { s0 -= EUC_KEEP * fmaf(q0n, q0n, x2); s1 -= EUC_KEEP * fmaf(q1n, q1n, x2); }
+                                s0 = fmaf(bnd, q0n, s0);
+                                s1 = fmaf(bnd, q1n, s1);
+                            }
+                            pass0 |= !(s0 < sh.tau[cb + c]) ? (1u << c) : 0u;
+                            pass1 |= !(s1 < sh.tau[cb + 32 + c]) ? (1u << c) : 0u;
                         }
-                        float sc = __uint_as_float(bits) * mul;
-                        if (FILTER) {
-                            const float qn = sh.qn[c];
-                            if (euclid) sc -= EUC_KEEP * fmaf(qn, qn, x2);
-                            sc = fmaf(bnd, qn, sc);
-                            if (sc != sc) sc = INFINITY;  // undecidable here: keep it, the exact rescoring judges
-                        } else if (sc != sc) {
-                            sc = -INFINITY;
-                        }
-                        if (sc >= sh.tau[c]) {
-                            int pos = atomicAdd(&sh.cnt[c], 1);
-                            if (pos < P) my_cand[(size_t)c * P + pos] = make_key(sc, (uint32_t)(p.row_base + row));
-                            else atomicExch(p.flags, 1);
+                        uint64_t pass = (uint64_t)pass0 | ((uint64_t)pass1 << 32);
+                        if (p.nq - cb < 64) pass &= (1ull << (p.nq - cb)) - 1ull;
+#pragma unroll 1
+                        while (pass) {
+                            const uint32_t c = (uint32_t)__ffsll((long long)pass) - 1u;
+                            pass &= pass - 1ull;
+                            uint32_t bits = 0;
+#pragma unroll
+                            for (uint32_t i = 0; i < 32; ++i) {  // register file is not indexable: select by compare
+                                if (c == i) bits = v0[i];
+                                if (c == 32 + i) bits = v1[i];
+                            }
+                            const uint32_t qi = cb + c;
+                            float sc = __uint_as_float(bits) * mul;
+                            if (FILTER) {
+                                const float qn = sh.qn[qi];
+                                if (euclid) sc -= EUC_KEEP * fmaf(qn, qn, x2);
+                                sc = fmaf(bnd, qn, sc);
+                                if (sc != sc) sc = INFINITY;  // undecidable here: keep it, the exact rescoring judges
+                            } else if (sc != sc) {
+                                sc = -INFINITY;
+                            }
+                            if (sc >= sh.tau[qi]) {
+                                int pos = atomicAdd(&sh.cnt[qi], 1);
+                                if (pos < P) my_cand[(size_t)qi * P + pos] = make_key(sc, (uint32_t)(p.row_base + row));
+                                else atomicExch(p.flags, 1);
+                            }
                         }
                     }
                 }
@@ -577,32 +587,31 @@ static int tc_debug_flags() {
     return dbg ? atoi(dbg) : 0;
 }
 
-template <int NT>
-static int launch_passes(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint32_t grid, uint32_t k_emit, float margin_c,
-                         const float *qhi, const float *qlo, const float *qnorm, uint32_t Qpad, const int *only_if,
-                         uint64_t *launches, bool count_main) {
+// One launch: queries [q0, q0+nq) against the whole shard, QT = 64 or 128 query columns per MMA.
+template <int NT, int QT>
+static int launch_pass(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint32_t grid, uint32_t k_emit, float margin_c,
+                       const float *qhi, const float *qlo, const float *qnorm, uint32_t Qpad, uint32_t q0, uint32_t nq,
+                       const int *only_if, uint64_t *launches, bool count_main) {
     using namespace tc;
     CUtensorMap map_rows, map_qhi, map_qlo;
     if (make_map(&map_rows, a.rows, a.n, a.dim, ROWS)) return -1;
-    if (make_map(&map_qhi, qhi, Qpad, a.dim, QT)) return -1;
+    if (make_map(&map_qhi, qhi, Qpad, a.dim, QT)) return -1;          // rows past Qpad are zero-filled by TMA
     if (make_map(&map_qlo, qlo ? qlo : qhi, Qpad, a.dim, QT)) return -1;
-    const size_t smem = (size_t)Cfg<NT>::RING_BYTES + sizeof(Shared) + 1024;
+    const size_t smem = (size_t)Cfg<NT, QT>::RING_BYTES + sizeof(Shared) + 1024;
     if (smem > di.max_smem_optin) {
         set_error("tensor path needs %zu B shared memory (> %zu)", smem, di.max_smem_optin);
         return -1;
     }
-    NK_CUDA_OK(cudaFuncSetAttribute(knn_scan_tc_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    for (uint32_t q0 = 0; q0 < a.Q; q0 += QT) {
-        Params p;
-        p.n = a.n; p.dim = a.dim; p.nslab = (a.dim + BK - 1) / BK; p.row_base = a.row_base;
-        p.q0 = q0; p.nq = a.Q - q0 < (uint32_t)QT ? a.Q - q0 : (uint32_t)QT; p.k = a.k;
-        p.metric = a.metric; p.k_emit = k_emit; p.margin_c = margin_c; p.qnorm = qnorm;
-        p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = only_if; p.debug = tc_debug_flags();
-        knn_scan_tc_kernel<NT><<<grid, THREADS, smem, a.stream>>>(map_rows, map_qhi, map_qlo, p);
-        NK_CUDA_OK(cudaGetLastError());
-        if (launches) ++*launches;
-        if (count_main && a.main_launches) ++*a.main_launches;
-    }
+    NK_CUDA_OK(cudaFuncSetAttribute(knn_scan_tc_kernel<NT, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    Params p;
+    p.n = a.n; p.dim = a.dim; p.nslab = (a.dim + BK - 1) / BK; p.row_base = a.row_base;
+    p.q0 = q0; p.nq = nq; p.k = a.k; p.qpad_off = q0;
+    p.metric = a.metric; p.k_emit = k_emit; p.margin_c = margin_c; p.qnorm = qnorm;
+    p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = only_if; p.debug = tc_debug_flags();
+    knn_scan_tc_kernel<NT, QT><<<grid, THREADS, smem, a.stream>>>(map_rows, map_qhi, map_qlo, p);
+    NK_CUDA_OK(cudaGetLastError());
+    if (launches) ++*launches;
+    if (count_main && a.main_launches) ++*a.main_launches;
     return 0;
 }
 
@@ -623,12 +632,12 @@ static void tc_print_prof(cudaStream_t stream, uint32_t num_tiles, uint32_t grid
 static int scan_tensor_exact(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *out_keys, uint64_t *launches,
                              const int *only_if, bool prep, bool count_main) {
     using namespace tc;
-    const uint32_t Qpad = (a.Q + QT - 1) / QT * QT;
+    const uint32_t Qpad = (a.Q + 63) / 64 * 64;
     const uint32_t num_tiles = (a.n + ROWS - 1) / ROWS;
     uint32_t grid = (uint32_t)di.num_sms;
     if (grid > num_tiles) grid = num_tiles;
-    if (ws_reserve((void **)&ws.qaux, &ws.qaux_bytes, ((size_t)2 * Qpad * a.dim + Qpad) * 4)) return -1;
-    if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)grid * QT * P * 8)) return -1;
+    if (ws_reserve((void **)&ws.qaux, &ws.qaux_bytes, ((size_t)2 * Qpad * a.dim + Qpad + QT_MAX) * 4)) return -1;
+    if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)grid * QT_MAX * P * 8)) return -1;
     if (ws_reserve((void **)&ws.partial, &ws.partial_bytes, (size_t)a.Q * grid * a.k * 8)) return -1;
     float *qhi = ws.qaux, *qlo = ws.qaux + (size_t)Qpad * a.dim, *qnorm = ws.qaux + (size_t)2 * Qpad * a.dim;
     if (prep) {
@@ -637,7 +646,10 @@ static int scan_tensor_exact(const DeviceInfo &di, const ScanArgs &a, Workspace 
         if (launches) ++*launches;
     }
     if (count_main && a.ev_begin) NK_CUDA_OK(cudaEventRecord(a.ev_begin, a.stream));
-    if (launch_passes<3>(di, a, ws, grid, a.k, 0.0f, qhi, qlo, nullptr, Qpad, only_if, launches, count_main)) return -1;
+    for (uint32_t q0 = 0; q0 < a.Q; q0 += 64) {
+        const uint32_t nq = a.Q - q0 < 64u ? a.Q - q0 : 64u;
+        if (launch_pass<3, 64>(di, a, ws, grid, a.k, 0.0f, qhi, qlo, nullptr, Qpad, q0, nq, only_if, launches, count_main)) return -1;
+    }
     if (count_main && a.ev_end) NK_CUDA_OK(cudaEventRecord(a.ev_end, a.stream));
     if (merge_keys(ws.partial, grid, a.k, (size_t)grid * a.k, a.Q, a.k, out_keys, a.stream, only_if)) return -1;
     if (launches) ++*launches;
@@ -663,7 +675,7 @@ int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
         set_error("tensor filter path: unsupported shape");
         return -1;
     }
-    const uint32_t Qpad = (a.Q + QT - 1) / QT * QT;
+    const uint32_t Qpad = (a.Q + 63) / 64 * 64;
     const uint32_t num_tiles = (a.n + ROWS - 1) / ROWS;
     uint32_t grid = (uint32_t)di.num_sms;
     if (grid > num_tiles) grid = num_tiles;
@@ -677,8 +689,8 @@ int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
     // 2^-10 (tf32 rounding of both operands) + d * 2^-22 (fp32 accumulation, truncating adders) + fp32 rounding of the norms
     const float margin_c = 9.765625e-4f + (float)a.dim * 2.384185791015625e-7f + 4e-6f;
 
-    if (ws_reserve((void **)&ws.qaux, &ws.qaux_bytes, ((size_t)2 * Qpad * a.dim + Qpad) * 4)) return -1;
-    if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)grid * QT * P * 8)) return -1;
+    if (ws_reserve((void **)&ws.qaux, &ws.qaux_bytes, ((size_t)2 * Qpad * a.dim + Qpad + QT_MAX) * 4)) return -1;
+    if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)grid * QT_MAX * P * 8)) return -1;
     if (ws_reserve((void **)&ws.partial, &ws.partial_bytes, (size_t)a.Q * grid * k_emit * 8)) return -1;
     if (ws_reserve((void **)&ws.keys2, &ws.keys2_bytes, (size_t)a.Q * c_out * 8)) return -1;
     float *qhi = ws.qaux, *qlo = ws.qaux + (size_t)Qpad * a.dim, *qnorm = ws.qaux + (size_t)2 * Qpad * a.dim;
@@ -690,7 +702,19 @@ int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
     NK_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
     if (a.ev_begin) NK_CUDA_OK(cudaEventRecord(a.ev_begin, a.stream));
-    if (launch_passes<1>(di, a, ws, grid, k_emit, margin_c, qhi, nullptr, qnorm, Qpad, nullptr, launches, true)) return -1;
+    // 128 query columns per MMA while more than 64 queries remain (twice the queries per corpus byte streamed),
+    // a 64-column launch for the tail
+    for (uint32_t q0 = 0; q0 < a.Q;) {
+        const uint32_t left = a.Q - q0;
+        if (left > 64) {
+            const uint32_t nq = left < 128u ? left : 128u;
+            if (launch_pass<1, 128>(di, a, ws, grid, k_emit, margin_c, qhi, nullptr, qnorm, Qpad, q0, nq, nullptr, launches, true)) return -1;
+            q0 += nq;
+        } else {
+            if (launch_pass<1, 64>(di, a, ws, grid, k_emit, margin_c, qhi, nullptr, qnorm, Qpad, q0, left, nullptr, launches, true)) return -1;
+            q0 += left;
+        }
+    }
     if (a.ev_end) NK_CUDA_OK(cudaEventRecord(a.ev_end, a.stream));
     if (merge_keys(ws.partial, grid, k_emit, (size_t)grid * k_emit, a.Q, c_out, ws.keys2, a.stream, nullptr, k_emit)) return -1;
     RescoreParams rp;
