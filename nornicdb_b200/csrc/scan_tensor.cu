@@ -412,15 +412,22 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                 }
             group_sync(EPI_BAR, EPI_THREADS);
         }
-        // emit this CTA's list per query: best k (exact) or everything inside the margin (filter)
-        for (uint32_t qi = quad; qi < p.nq; qi += 4) {
+    }
+
+    // ---- emit this CTA's list per query: best k (exact) or everything inside the margin (filter).  Every role has
+    // finished its tile loop here, so all 16 warps share the final prunes (4x shorter tail than the epilogue warps alone).
+    __syncthreads();
+    {
+        const bool cosine = p.metric == NK_METRIC_COSINE;
+        uint64_t *my_cand = p.cand + (size_t)blockIdx.x * QT * P;
+        for (uint32_t qi = warp; qi < p.nq; qi += THREADS / 32) {
             const float margin2 = !FILTER ? 0.0f : filter_margin2(p.metric, p.margin_c, __uint_as_float(sh.maxxx), sh.qn[qi]);
             warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane,
                            p.partial + ((size_t)(p.q0 + qi) * gridDim.x + blockIdx.x) * p.k_emit, (int)p.k_emit, FILTER, margin2, (int)p.k_emit);
             // the emitted list was cut at k_emit while rows inside the margin remained -> exact fallback
             if (FILTER && lane == 0 && sh.cnt[qi] >= (int)p.k_emit && (int)p.k_emit > (int)p.k) atomicExch(p.flags + 1, 1);
         }
-        if (FILTER && !cosine && tid == EPI_WARP0 * 32) atomicMax(reinterpret_cast<unsigned int *>(p.flags + 2), sh.maxxx);
+        if (FILTER && !cosine && tid == 0) atomicMax(reinterpret_cast<unsigned int *>(p.flags + 2), sh.maxxx);
     }
 
     if (prof && tid == EPI_WARP0 * 32) { g_tc_prof[17] = acc_a; g_tc_prof[18] = clock64() - t_start; g_tc_prof[19] = (long long)num_tiles; }

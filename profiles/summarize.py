@@ -85,13 +85,19 @@ def ncu_summary(rep, md_path, title, algorithmic_bytes=None):
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     launches(os.path.join(G, f"launches_{tag}_headline.csv"), os.path.join(OUT, f"launches_{tag}_headline.md"),
-             f"Launch list, round {tag[1:]}: bench.py headline (N=10M d=1024 Q=64 k=10 cosine), tensor-core path")
+             f"Launch list, round {tag[1:]}: bench.py headline (N=10M d=1024 Q=64 k=10 cosine), tensor-core filter path")
+    if os.path.exists(os.path.join(G, f"launches_{tag}_c2_filter.csv")):
+        launches(os.path.join(G, f"launches_{tag}_c2_filter.csv"), os.path.join(OUT, f"launches_{tag}_c2_filter.md"),
+                 f"Launch list, round {tag[1:]}: bench.py c2 (N=1M d=1024 Q=64 k=10 cosine), tensor-core filter path")
     if os.path.exists(os.path.join(G, f"launches_{tag}_simt.csv")):
         launches(os.path.join(G, f"launches_{tag}_simt.csv"), os.path.join(OUT, f"launches_{tag}_c2_simt.md"),
                  f"Launch list, round {tag[1:]}: bench.py c2 (N=1M d=1024 Q=64 k=10 cosine), CUDA-core path (first working version)")
     t = {}
-    t["headline:tensor"] = ncu_summary(os.path.join(G, f"prof_{tag}_tc_headline.ncu-rep"), os.path.join(OUT, f"ncu_{tag}_scan_tc_headline.md"),
-                                       "knn_scan_tc_kernel — N=10M d=1024 fp32 Q=64 k=10 cosine", 10_000_000 * 1024 * 4)
+    t["headline:filter"] = ncu_summary(os.path.join(G, f"prof_{tag}_tc_headline.ncu-rep"), os.path.join(OUT, f"ncu_{tag}_scan_tc_filter_headline.md"),
+                                       "knn_scan_tc_kernel<1,64> (1xTF32 filter) — N=10M d=1024 fp32 Q=64 k=10 cosine", 10_000_000 * 1024 * 4)
+    if os.path.exists(os.path.join(G, f"prof_{tag}_tc3_headline.ncu-rep")):
+        t["headline:tensor"] = ncu_summary(os.path.join(G, f"prof_{tag}_tc3_headline.ncu-rep"), os.path.join(OUT, f"ncu_{tag}_scan_tc_exact_headline.md"),
+                                           "knn_scan_tc_kernel<3,64> (3xTF32 exact) — N=10M d=1024 fp32 Q=64 k=10 cosine", 10_000_000 * 1024 * 4)
     t["q1:simt"] = ncu_summary(os.path.join(G, f"prof_{tag}_simt_q1.ncu-rep"), os.path.join(OUT, f"ncu_{tag}_scan_simt_q1.md"),
                                "knn_scan_simt_kernel — N=10M d=1024 fp32 Q=1 k=10 cosine", 10_000_000 * 1024 * 4)
     t["c4:simt"] = ncu_summary(os.path.join(G, f"prof_{tag}_simt_c4.ncu-rep"), os.path.join(OUT, f"ncu_{tag}_scan_simt_c4.md"),
