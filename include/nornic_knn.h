@@ -91,7 +91,10 @@ enum { NK_DTYPE_F32 = 0, NK_DTYPE_F16 = 1 };
  * rescoring (device-side fallback to the exact scan on margin overflow). */
 enum { NK_PATH_AUTO = 0, NK_PATH_SIMT = 1, NK_PATH_TENSOR = 2, NK_PATH_TENSOR_FILTER = 3 };
 
+/* k up to NK_MAX_K is one fused pass; larger k (the reference accepts any k) is served by ceil(k/NK_MAX_K) passes
+ * of the CUDA-core scan, up to NK_MAX_K_TOTAL results per query. */
 #define NK_MAX_K 1024u
+#define NK_MAX_K_TOTAL 65536u
 
 typedef struct NkIndex NkIndex;
 
@@ -173,7 +176,9 @@ int nk_search_device(NkIndex *ix, const float *queries_dev, uint32_t Q, uint32_t
 int nk_search_keys_device(NkIndex *ix, const float *queries_dev, uint32_t Q, uint32_t k, uint64_t *out_keys_dev,
                           void *stream);
 /* Merge n_lists candidate lists laid out [n_lists][Q][k] into final [Q x k] idx/score on the current
- * device of `device_id`.  metric selects the score decoding (euclidean: distance). */
+ * device of `device_id`.  metric selects the score decoding (euclidean: distance).  With a stream the call is
+ * asynchronous on it (the searches that produced the keys must be ordered before it on that stream); with
+ * stream == NULL it synchronises the device first and returns after the merge has completed. */
 int nk_merge_keys_device(int device_id, const uint64_t *keys_dev, uint32_t n_lists, uint32_t Q, uint32_t k,
                          int metric, uint32_t *out_idx_dev, float *out_score_dev, void *stream);
 

@@ -95,7 +95,36 @@ static NkShard *find_shard(NkIndex *ix, uint64_t row, uint64_t *local) {
 }
 
 static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uint32_t k, uint64_t *out_keys,
+                    cudaStream_t stream);
+
+// k > NK_MAX_K (the reference accepts any k, cuda_bridge.go:327-375): ceil(k / NK_MAX_K) fused CUDA-core passes; pass p+1
+// only admits keys strictly below the last key pass p returned, so the passes tile the ranking exactly.
+static int run_scan_bigk(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uint32_t k, uint64_t *out_keys,
+                         cudaStream_t stream, const void *rows = nullptr, uint32_t n_rows = 0, bool custom_rows = false) {
+    if (nk::ws_reserve((void **)&s.ws.below, &s.ws.below_bytes, (size_t)Q * 8)) return -1;
+    if (nk::ws_reserve((void **)&s.ws.keys2, &s.ws.keys2_bytes, (size_t)Q * NK_MAX_K * 8)) return -1;
+    NK_CUDA_OK(cudaMemsetAsync(s.ws.below, 0xff, (size_t)Q * 8, stream));
+    for (uint32_t done = 0; done < k;) {
+        const uint32_t kp = k - done < NK_MAX_K ? k - done : NK_MAX_K;
+        nk::ScanArgs a;
+        a.rows = custom_rows ? rows : s.rows; a.dtype = ix->dtype; a.n = custom_rows ? n_rows : (uint32_t)s.n; a.dim = ix->dim;
+        a.row_base = custom_rows ? 0 : s.base;
+        a.queries = q_dev; a.Q = Q; a.k = kp; a.metric = ix->metric; a.stream = stream; a.below = s.ws.below;
+        if (nk::scan_simt(s.di, a, s.ws, s.ws.keys2, &ix->stats.kernel_launches)) return -1;
+        NK_CUDA_OK(cudaMemcpy2DAsync(out_keys + done, (size_t)k * 8, s.ws.keys2, (size_t)kp * 8, (size_t)kp * 8, Q,
+                                     cudaMemcpyDeviceToDevice, stream));
+        if (nk::update_below(s.ws.keys2, Q, kp, s.ws.below, stream)) return -1;
+        ix->stats.kernel_launches++;
+        ix->stats.bytes_scanned += (uint64_t)s.n * ix->dim * ix->esz() * ((Q + 7) / 8);
+        done += kp;
+    }
+    ix->last_path = NK_PATH_SIMT;
+    return 0;
+}
+
+static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uint32_t k, uint64_t *out_keys,
                     cudaStream_t stream) {
+    if (k > NK_MAX_K) return run_scan_bigk(ix, s, q_dev, Q, k, out_keys, stream);
     nk::ScanArgs a;
     a.rows = s.rows; a.dtype = ix->dtype; a.n = (uint32_t)s.n; a.dim = ix->dim; a.row_base = s.base;
     a.queries = q_dev; a.Q = Q; a.k = k; a.metric = ix->metric; a.stream = stream;
@@ -416,7 +445,7 @@ int nk_search(NkIndex *ix, const float *queries_host, uint32_t Q, uint32_t k, ui
     if (k == 0 || N == 0 || Q == 0) return 0;  // cuda_bridge.go:644-646, gpu.go:1540-1542
     if (!queries_host || !out_idx || !out_score) { nk::set_error("null argument"); return -1; }
     const uint32_t ke = k > N ? (uint32_t)N : k;  // cuda_bridge.go:647-649
-    if (ke > NK_MAX_K) { nk::set_error("k=%u exceeds NK_MAX_K=%u", ke, NK_MAX_K); return -1; }
+    if (ke > NK_MAX_K_TOTAL) { nk::set_error("k=%u exceeds NK_MAX_K_TOTAL=%u", ke, NK_MAX_K_TOTAL); return -1; }
     const size_t qbytes = (size_t)Q * ix->dim * sizeof(float);
     ix->stats.searches++;
     ix->stats.queries += Q;
@@ -507,7 +536,7 @@ int nk_search_keys_device(NkIndex *ix, const float *queries_dev, uint32_t Q, uin
     if (single_shard(ix, &s)) return -1;
     if (k == 0 || Q == 0) return 0;
     if (!queries_dev || !out_keys_dev) { nk::set_error("null argument"); return -1; }
-    if (k > NK_MAX_K) { nk::set_error("k=%u exceeds NK_MAX_K=%u", k, NK_MAX_K); return -1; }
+    if (k > NK_MAX_K_TOTAL) { nk::set_error("k=%u exceeds NK_MAX_K_TOTAL=%u", k, NK_MAX_K_TOTAL); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
     NK_CUDA_OK(cudaSetDevice(s->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
@@ -529,7 +558,7 @@ int nk_search_device(NkIndex *ix, const float *queries_dev, uint32_t Q, uint32_t
     if (k == 0 || N == 0 || Q == 0) return 0;
     if (!queries_dev || !out_idx_dev || !out_score_dev) { nk::set_error("null argument"); return -1; }
     if (k > N) { nk::set_error("nk_search_device: k=%u > rows=%llu (clamp on the host side)", k, (unsigned long long)N); return -1; }
-    if (k > NK_MAX_K) { nk::set_error("k=%u exceeds NK_MAX_K=%u", k, NK_MAX_K); return -1; }
+    if (k > NK_MAX_K_TOTAL) { nk::set_error("k=%u exceeds NK_MAX_K_TOTAL=%u", k, NK_MAX_K_TOTAL); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
     NK_CUDA_OK(cudaSetDevice(s->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
@@ -542,17 +571,27 @@ int nk_search_device(NkIndex *ix, const float *queries_dev, uint32_t Q, uint32_t
     return (int)k;
 }
 
+// grow-only per-device scratch of nk_merge_keys_device (no allocation per merge)
+static std::mutex g_merge_mu;
+static uint64_t *g_merge_scratch[64] = {nullptr};
+static size_t g_merge_scratch_bytes[64] = {0};
+
 int nk_merge_keys_device(int device_id, const uint64_t *keys_dev, uint32_t n_lists, uint32_t Q, uint32_t k, int metric,
                          uint32_t *out_idx_dev, float *out_score_dev, void *stream) {
     if (k == 0 || Q == 0 || n_lists == 0) return 0;
     if (!keys_dev || !out_idx_dev || !out_score_dev) { nk::set_error("null argument"); return -1; }
+    if (device_id < 0 || device_id >= 64) { nk::set_error("bad device id %d", device_id); return -1; }
     NK_CUDA_OK(cudaSetDevice(device_id));
     cudaStream_t st = (cudaStream_t)stream;
-    uint64_t *merged = nullptr;
-    NK_CUDA_OK(cudaMallocAsync((void **)&merged, (size_t)Q * k * 8, st));
+    // No stream given: behave synchronously (the producers may have run on the indexes' own non-blocking streams,
+    // which the legacy default stream does not order against).
+    if (!st) NK_CUDA_OK(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_merge_mu);
+    if (nk::ws_reserve((void **)&g_merge_scratch[device_id], &g_merge_scratch_bytes[device_id], (size_t)Q * k * 8)) return -1;
+    uint64_t *merged = g_merge_scratch[device_id];
     int rc = nk::merge_keys(keys_dev, n_lists, (size_t)Q * k, k, Q, k, merged, st);
     if (rc == 0) rc = nk::decode_keys(merged, Q, k, metric, out_idx_dev, out_score_dev, st);
-    cudaFreeAsync(merged, st);
+    if (rc == 0 && !st) NK_CUDA_OK(cudaStreamSynchronize(st));
     return rc;
 }
 
@@ -563,7 +602,7 @@ int nk_score_subset(NkIndex *ix, const float *query_host, const uint32_t *rows_h
     if (n_subset == 0 || k == 0) return 0;
     if (!query_host || !rows_host || !out_idx || !out_score) { nk::set_error("null argument"); return -1; }
     const uint32_t ke = std::min(k, n_subset);
-    if (ke > NK_MAX_K) { nk::set_error("k=%u exceeds NK_MAX_K=%u", ke, NK_MAX_K); return -1; }
+    if (ke > NK_MAX_K_TOTAL) { nk::set_error("k=%u exceeds NK_MAX_K_TOTAL=%u", ke, NK_MAX_K_TOTAL); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
     for (uint32_t i = 0; i < n_subset; ++i)
         if (rows_host[i] < ix->row_base || rows_host[i] - ix->row_base >= s->n) {
@@ -591,7 +630,9 @@ int nk_score_subset(NkIndex *ix, const float *query_host, const uint32_t *rows_h
         nk::ScanArgs a;
         a.rows = d_gather; a.dtype = ix->dtype; a.n = n_subset; a.dim = ix->dim; a.row_base = 0;
         a.queries = s->ws.queries; a.Q = 1; a.k = ke; a.metric = ix->metric; a.stream = s->stream;
-        if (nk::scan_simt(s->di, a, s->ws, s->ws.keys, &ix->stats.kernel_launches)) { rc = -1; break; }
+        if (ke > NK_MAX_K) {  // ScoreSubset ranks every candidate (up to MaxCandidates = 5000, vector_pipeline.go:24-31)
+            if (run_scan_bigk(ix, *s, s->ws.queries, 1, ke, s->ws.keys, s->stream, d_gather, n_subset, true)) { rc = -1; break; }
+        } else if (nk::scan_simt(s->di, a, s->ws, s->ws.keys, &ix->stats.kernel_launches)) { rc = -1; break; }
         if (nk::decode_keys(s->ws.keys, 1, ke, ix->metric, s->ws.out_idx, s->ws.out_score, s->stream)) { rc = -1; break; }
         if (cudaMemcpyAsync(pos.data(), s->ws.out_idx, (size_t)ke * 4, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) { rc = -1; break; }
         if (cudaMemcpyAsync(out_score, s->ws.out_score, (size_t)ke * 4, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) { rc = -1; break; }

@@ -18,6 +18,7 @@ struct Workspace {
     uint64_t *cand = nullptr;     size_t cand_bytes = 0;     // [grid][QT][cap] candidate buffers
     uint64_t *partial = nullptr;  size_t partial_bytes = 0;  // [Q][grid][k] per-CTA sorted lists
     uint64_t *keys = nullptr;     size_t keys_bytes = 0;     // [Q][k] merged keys
+    uint64_t *below = nullptr;    size_t below_bytes = 0;    // [Q] exclusion bounds of the k > NK_MAX_K passes
     uint64_t *keys2 = nullptr;    size_t keys2_bytes = 0;    // [Q][c_out] filter-mode candidates (by upper bound)
     float *queries = nullptr;     size_t queries_bytes = 0;  // staged queries (host API)
     uint32_t *out_idx = nullptr;  size_t out_idx_bytes = 0;
@@ -45,6 +46,9 @@ struct ScanArgs {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     uint64_t *main_launches = nullptr;
     const int *only_if = nullptr;  // CUDA-core scan as a device-side conditional fallback (runs only if *only_if != 0)
+    // k > NK_MAX_K is served by repeated passes: pass p only admits keys strictly below below[q] (the last key the
+    // previous pass returned for query q); nullptr = no bound.  CUDA-core scan only.
+    const uint64_t *below = nullptr;
 };
 
 // Fused distance + top-k scan on CUDA cores (small Q, any dim / dtype / alignment).
@@ -66,7 +70,9 @@ int normalize_rows(float *rows, uint32_t n, uint32_t dim, cudaStream_t s);
 int row_scores(const float *rows, const float *query, float *scores, uint32_t n, uint32_t dim, int normalized,
                cudaStream_t s);
 int topk_scores(const DeviceInfo &di, const float *scores, uint32_t n, uint32_t k, Workspace &ws, uint64_t *out_keys,
-                cudaStream_t s);
+                cudaStream_t s, const uint64_t *below = nullptr);
+// below[q] = keys[q*k + k-1] (the smallest key pass p returned): the exclusion bound of pass p+1.
+int update_below(const uint64_t *keys, uint32_t Q, uint32_t k, uint64_t *below, cudaStream_t s);
 int fill_uniform(void *out, int dtype, uint64_t n_rows, uint32_t dim, uint64_t seed, uint64_t row_base, cudaStream_t s);
 int gather_rows(const void *rows, int dtype, uint32_t dim, const uint32_t *idx, uint32_t n_idx, void *out,
                 cudaStream_t s);

@@ -223,10 +223,23 @@ int cuda_topk(CudaDevice *dev, CudaBuffer *scores, unsigned int *out_indices, fl
     std::lock_guard<std::mutex> lk(dev->mu);
     NK_CUDA_OK(cudaSetDevice(dev->device_id));
     nk::Workspace &ws = dev->ws;
+    if (k > NK_MAX_K_TOTAL) { nk::set_error("k=%u exceeds NK_MAX_K_TOTAL=%u", k, NK_MAX_K_TOTAL); return -1; }
     if (nk::ws_reserve((void **)&ws.keys, &ws.keys_bytes, (size_t)k * 8)) return -1;
     if (nk::ws_reserve((void **)&ws.out_idx, &ws.out_idx_bytes, (size_t)k * 4)) return -1;
     if (nk::ws_reserve((void **)&ws.out_score, &ws.out_score_bytes, (size_t)k * 4)) return -1;
-    if (nk::topk_scores(dev->info, scores->data, n, k, ws, ws.keys, dev->stream)) return -1;
+    if (k <= NK_MAX_K) {
+        if (nk::topk_scores(dev->info, scores->data, n, k, ws, ws.keys, dev->stream)) return -1;
+    } else {
+        // any k (cuda_bridge.go:327-375): passes of NK_MAX_K, each bounded above by the previous pass's last key
+        if (nk::ws_reserve((void **)&ws.below, &ws.below_bytes, 8)) return -1;
+        NK_CUDA_OK(cudaMemsetAsync(ws.below, 0xff, 8, dev->stream));
+        for (unsigned int done = 0; done < k;) {
+            const unsigned int kp = k - done < NK_MAX_K ? k - done : NK_MAX_K;
+            if (nk::topk_scores(dev->info, scores->data, n, kp, ws, ws.keys + done, dev->stream, ws.below)) return -1;
+            if (nk::update_below(ws.keys + done, 1, kp, ws.below, dev->stream)) return -1;
+            done += kp;
+        }
+    }
     if (nk::decode_keys(ws.keys, 1, k, NK_METRIC_DOT, ws.out_idx, ws.out_score, dev->stream)) return -1;
     NK_CUDA_OK(cudaMemcpyAsync(out_indices, ws.out_idx, (size_t)k * 4, cudaMemcpyDeviceToHost, dev->stream));
     NK_CUDA_OK(cudaMemcpyAsync(out_scores, ws.out_score, (size_t)k * 4, cudaMemcpyDeviceToHost, dev->stream));

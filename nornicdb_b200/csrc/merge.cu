@@ -33,7 +33,13 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(MergeParams p
     const uint64_t total = (uint64_t)p.n_lists * p.list_len;
     const int tid = threadIdx.x;
 
-    for (int i = tid; i < MERGE_P; i += MERGE_THREADS) sbuf[i] = 0ull;
+    // sort width: the whole input when it fits a smaller power of two (cross-GPU merges fold a few dozen keys)
+    int P = MERGE_P;
+    if (total <= (uint64_t)MERGE_P) {
+        P = 64;
+        while ((uint64_t)P < total || P < (int)p.k) P <<= 1;
+    }
+    for (int i = tid; i < P; i += MERGE_THREADS) sbuf[i] = 0ull;
     if (tid == 0) s_fill = 0;
     __syncthreads();
 
@@ -41,7 +47,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(MergeParams p
     uint64_t pos = 0;
     while (pos < total) {
         // fill slots [fill, MERGE_P) with keys that can still matter
-        const uint64_t room_all = MERGE_P - (uint64_t)s_fill;
+        const uint64_t room_all = (uint64_t)P - (uint64_t)s_fill;
         __syncthreads();
         const int fill0 = s_fill;
         uint64_t chunk = total - pos;
@@ -59,9 +65,9 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(MergeParams p
         __syncthreads();
         const int filled = s_fill;
         // sort only when the buffer is nearly full or the input is exhausted
-        if (pos >= total || filled > MERGE_P - MERGE_THREADS) {
-            for (int i = filled + tid; i < MERGE_P; i += MERGE_THREADS) sbuf[i] = 0ull;
-            block_bitonic_sort_desc(sbuf, MERGE_P);
+        if (pos >= total || filled > P - MERGE_THREADS) {
+            for (int i = filled + tid; i < P; i += MERGE_THREADS) sbuf[i] = 0ull;
+            block_bitonic_sort_desc(sbuf, P);
             int keep = filled < (int)p.k ? filled : (int)p.k;
             if (filled >= (int)p.k) kth = sbuf[p.k - 1];
             __syncthreads();
@@ -115,7 +121,8 @@ constexpr int TOPK_THREADS = 256;
 constexpr int TOPK_IV = 1024;  // scores per CTA between prune checks
 
 __global__ void __launch_bounds__(TOPK_THREADS) topk_scores_kernel(const float *scores, uint32_t n, uint32_t k, int P,
-                                                                   uint64_t *cand, uint64_t *partial, int *flags) {
+                                                                   uint64_t *cand, uint64_t *partial, int *flags,
+                                                                   const uint64_t *below) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *sbuf = reinterpret_cast<uint64_t *>(smem_raw);
     __shared__ float s_tau;
@@ -132,9 +139,12 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_scores_kernel(const float *
             float s = scores[i];
             if (s != s) s = -INFINITY;
             if (s >= s_tau) {
-                int pos = atomicAdd(&s_cnt, 1);
-                if (pos < P) my[pos] = make_key(s, i);
-                else atomicExch(flags, 1);
+                const uint64_t key = make_key(s, i);
+                if (!below || key < below[0]) {
+                    int pos = atomicAdd(&s_cnt, 1);
+                    if (pos < P) my[pos] = key;
+                    else atomicExch(flags, 1);
+                }
             }
         }
         __syncthreads();
@@ -146,8 +156,18 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_scores_kernel(const float *
     for (uint32_t i = threadIdx.x; i < k; i += TOPK_THREADS) partial[(size_t)blockIdx.x * k + i] = sbuf[i];
 }
 
+__global__ void update_below_kernel(const uint64_t *keys, uint32_t Q, uint32_t k, uint64_t *below) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < Q) below[q] = keys[(size_t)q * k + k - 1];  // 0 when the pass ran dry: nothing is below key 0
+}
+int update_below(const uint64_t *keys, uint32_t Q, uint32_t k, uint64_t *below, cudaStream_t s) {
+    update_below_kernel<<<(Q + 127) / 128, 128, 0, s>>>(keys, Q, k, below);
+    NK_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int topk_scores(const DeviceInfo &di, const float *scores, uint32_t n, uint32_t k, Workspace &ws, uint64_t *out_keys,
-                cudaStream_t s) {
+                cudaStream_t s, const uint64_t *below) {
     if (n == 0 || k == 0) return 0;
     if (k > NK_MAX_K) {
         set_error("k=%u exceeds NK_MAX_K=%u", k, NK_MAX_K);
@@ -161,7 +181,7 @@ int topk_scores(const DeviceInfo &di, const float *scores, uint32_t n, uint32_t 
     if (ws_reserve((void **)&ws.partial, &ws.partial_bytes, (size_t)grid * k * 8)) return -1;
     size_t smem = (size_t)P * 8;
     NK_CUDA_OK(cudaFuncSetAttribute(topk_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    topk_scores_kernel<<<grid, TOPK_THREADS, smem, s>>>(scores, n, k, P, ws.cand, ws.partial, ws.flags);
+    topk_scores_kernel<<<grid, TOPK_THREADS, smem, s>>>(scores, n, k, P, ws.cand, ws.partial, ws.flags, below);
     NK_CUDA_OK(cudaGetLastError());
     return merge_keys(ws.partial, grid, k, 0, 1, k, out_keys, s);
 }

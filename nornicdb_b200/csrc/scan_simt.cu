@@ -37,6 +37,7 @@ struct SimtParams {
     uint64_t *partial;   // [Q][grid][k]
     int *flags;
     const int *only_if;  // device-side conditional fallback: run only if *only_if != 0
+    const uint64_t *below;  // per-query exclusive key bound (k > NK_MAX_K passes) or nullptr
 };
 
 // ---- element loaders -------------------------------------------------------------------------
@@ -218,11 +219,12 @@ __global__ void __launch_bounds__(SIMT_THREADS) knn_scan_simt_kernel(SimtParams 
                 }
                 if (s != s) s = -INFINITY;
                 if (s >= s_tau[qi]) {
-                    int pos = atomicAdd(&s_cnt[qi], 1);
-                    if (pos < p.P)
-                        my_cand[(size_t)qi * p.P + pos] = make_key(s, (uint32_t)(p.row_base + row));
-                    else
-                        atomicExch(p.flags, 1);
+                    const uint64_t key = make_key(s, (uint32_t)(p.row_base + row));
+                    if (!p.below || key < p.below[p.q0 + qi]) {
+                        int pos = atomicAdd(&s_cnt[qi], 1);
+                        if (pos < p.P) my_cand[(size_t)qi * p.P + pos] = key;
+                        else atomicExch(p.flags, 1);
+                    }
                 }
             }
         }
@@ -329,7 +331,7 @@ int scan_simt(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *
         SimtParams p;
         p.rows = a.rows; p.n = a.n; p.dim = a.dim; p.row_base = a.row_base;
         p.queries = a.queries; p.q0 = q0; p.nq = left < (uint32_t)qt ? left : (uint32_t)qt; p.k = a.k;
-        p.metric = a.metric; p.P = P; p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = a.only_if;
+        p.metric = a.metric; p.P = P; p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = a.only_if; p.below = a.below;
         kern<<<grid_used, SIMT_THREADS, smem, a.stream>>>(p);
         NK_CUDA_OK(cudaGetLastError());
         if (launches) ++*launches;

@@ -230,7 +230,9 @@ def test_stats_and_device_api(knn_lib, oracle_mod):
     qd = torch.from_numpy(q).cuda()
     oi_d = torch.empty((Q, k), dtype=torch.int32, device="cuda")
     os_d = torch.empty((Q, k), dtype=torch.float32, device="cuda")
-    st = torch.cuda.current_stream().cuda_stream
+    stream = torch.cuda.Stream()  # an explicit stream: handle 0 means "the index's own stream" to the C ABI
+    torch.cuda.current_stream().synchronize()
+    st = stream.cuda_stream
     assert ix.search_device(qd.data_ptr(), Q, k, oi_d.data_ptr(), os_d.data_ptr(), st) == k
     torch.cuda.synchronize()
     gi, gs = ix.search(q, k)
@@ -254,3 +256,35 @@ def test_stats_and_device_api(knn_lib, oracle_mod):
     s = ix.stats()
     assert s["rows"] == n and s["searches"] >= 2 and s["kernel_launches"] > 0 and s["bytes_scanned"] >= n * d * 4
     ix.release()
+
+
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_k_beyond_one_pass(knn_lib, oracle_mod, metric):
+    # the reference accepts any k (cuda_bridge.go:327-375): k > NK_MAX_K is served by repeated bounded passes
+    rows_n, d = 9000, 48
+    run_case(oracle_mod, rows_n, d, 3, 2500, metric)
+    run_case(oracle_mod, rows_n, d, 1, rows_n, metric)  # full ranking, k == n
+
+
+def test_legacy_topk_any_k(gpu_device, oracle_mod):
+    rng = np.random.default_rng(5)
+    scores = rng.integers(-500, 500, 20000).astype(np.float32) / 16.0
+    s = gpu_device.NewBuffer(scores)
+    idx, sc = gpu_device.TopK(s, 20000, 3000)
+    oi, os_ = oracle_mod.topk_insertion(scores, 3000)
+    assert (idx == oi).all() and (sc == os_).all()
+    s.Release()
+
+
+def test_score_subset_large(knn_lib, oracle_mod):
+    from nornicdb_b200.knn import KnnIndex
+    rows = oracle_mod.fill_uniform(8000, 64, 31)
+    q = oracle_mod.fill_uniform(1, 64, 32)[0]
+    subset = np.random.default_rng(4).choice(8000, 3000, replace=False).astype(np.uint32)
+    ix = KnnIndex(64)
+    ix.upload(rows)
+    gi, gs = ix.score_subset(q, subset)  # ranks all 3000 candidates (> NK_MAX_K)
+    ix.release()
+    ex = oracle_mod.scores_exact64(rows[subset], q, "cosine")
+    order = np.argsort(-ex, kind="stable")
+    assert (gi == subset[order]).all()
