@@ -38,6 +38,8 @@ WORKLOADS = {
     "c2": (1_000_000, 1024, "f32", 64, 10, "cosine", "configs[1]: N=1M d=1024 (bge-m3) fp32 Q=64 k=10 cosine"),
     "c3": (10_000_000, 1024, "f32", 1024, 100, "dot", "configs[2]: N=10M d=1024 fp32 Q=1024 k=100 inner-product"),
     "c4": (10_000_000, 768, "f16", 1, 10, "euclidean", "configs[3]: N=10M d=768 fp16 Q=1 k=10 L2"),
+    "c5": (100_000_000, 1024, "f32", 1024, 10, "cosine",
+           "configs[4]: N=100M d=1024 fp32 Q=1024 k=10 cosine, row-sharded (needs >= 4 GPUs: 410 GB of corpus)"),
     "c1": (100_000, 128, "f32", 1, 10, "cosine", "configs[0]: N=100k d=128 fp32 Q=1 k=10 cosine"),
     "q1": (10_000_000, 1024, "f32", 1, 10, "cosine", "N=10M d=1024 fp32 Q=1 k=10 cosine (single-query latency)"),
 }
@@ -216,6 +218,10 @@ def main():
             sys.exit(2)
         G = world
     elem = 2 if dtype == "f16" else 4
+    if N_total // max(G, 1) * dim * elem > 150e9:
+        if rank == 0:
+            print(json.dumps({"error": f"workload {args.workload} needs more GPUs: {N_total // max(G, 1) * dim * elem / 1e9:.0f} GB per GPU"}))
+        return
     config = {"workload": desc, "N": N_total, "dim": dim, "corpus_dtype": dtype, "Q": Q, "k": k, "metric": metric,
               "sharding": f"row-range x{G}" if G > 1 else "single GPU",
               "l2": "corpus shard per GPU >> 126 MB L2 (inputs larger than L2; no flush needed)"

@@ -288,3 +288,42 @@ def test_score_subset_large(knn_lib, oracle_mod):
     ex = oracle_mod.scores_exact64(rows[subset], q, "cosine")
     order = np.argsort(-ex, kind="stable")
     assert (gi == subset[order]).all()
+
+
+def test_multi_device_index_in_one_process(knn_lib, oracle_mod):
+    """nk_index_create over several GPUs of this process: rows are range-sharded, every shard scans asynchronously,
+    the Q*k candidate keys come back over PCIe and are merged on the host (small-Q form)."""
+    from nornicdb_b200 import cuda
+    from nornicdb_b200.knn import KnnIndex
+    G = min(cuda.DeviceCount(), 4)
+    if G < 2:
+        pytest.skip("needs >= 2 GPUs in this process")
+    n, d, Q, k = 30_001, 128, 20, 25
+    rows = oracle_mod.fill_uniform(n, d, 42)
+    q = oracle_mod.fill_uniform(Q, d, 1337)
+    for metric in ("cosine", "euclidean"):
+        ix = KnnIndex(d, metric=metric, devices=tuple(range(G)))
+        ix.upload(rows)
+        assert len(ix) == n and (ix.read_rows(n // 2 - 3, 6) == rows[n // 2 - 3:n // 2 + 3]).all()
+        gi, gs = ix.search(q, k)
+        oi, os_ = oracle_mod.knn_exact64(rows, q, k, metric)
+        check_parity(rows, q, k, metric, gi, gs, oi, os_)
+        one = KnnIndex(d, metric=metric, devices=(0,))
+        one.upload(rows)
+        si, ss = one.search(q, k)
+        assert (si == gi).all() and np.allclose(ss, gs, rtol=2e-6, atol=1e-6)  # independent of the sharding
+        # append goes to the last shard; remove swaps across shards
+        extra = oracle_mod.fill_uniform(50, d, 99)
+        ix.append(extra)
+        ix.remove_swap(5)
+        host = np.concatenate([rows, extra])
+        host[5] = host[-1]
+        host = host[:-1]
+        gi, gs = ix.search(q, k)
+        oi, os_ = oracle_mod.knn_exact64(host, q, k, metric)
+        check_parity(host, q, k, metric, gi, gs, oi, os_)
+        ix.release(); one.release()
+    ix = KnnIndex(d, metric="cosine", devices=tuple(range(G)))
+    ix.fill_uniform(n, 42)  # device-side generation is shard-aware: same global stream
+    assert (ix.read_rows(0, n) == rows).all()
+    ix.release()
