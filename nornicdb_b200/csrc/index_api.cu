@@ -128,9 +128,10 @@ static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uin
     nk::ScanArgs a;
     a.rows = s.rows; a.dtype = ix->dtype; a.n = (uint32_t)s.n; a.dim = ix->dim; a.row_base = s.base;
     a.queries = q_dev; a.Q = Q; a.k = k; a.metric = ix->metric; a.stream = stream;
-    // AUTO: one CUDA-core launch serves up to 8 queries at the HBM roofline; from 9 queries on a second
-    // pass over the corpus would be needed, so the tensor-core filter scan (1xTF32 + exact rescoring, 64-128 queries
-    // per pass) takes over where it applies, else the exact 3xTF32 scan, else CUDA cores.
+    // AUTO (measured, N=10M d=1024, ms per batch: CUDA-core 5.9 / 6.2 / 6.1 / 7.6 at Q = 1 / 2 / 4 / 8, tensor filter 5.8-5.9
+    // for any Q <= 64): the CUDA-core scan keeps Q <= 4 (no prep / rescoring kernels, lowest latency on small corpora);
+    // from 5 queries on its 8-query variant drops to 82% of the roofline, so the tensor-core filter scan (1xTF32 + exact
+    // rescoring, 64-128 queries per pass) takes over where it applies, else the exact 3xTF32 scan, else CUDA cores.
     const bool tensor_ok = nk::scan_tensor_supported(s.di, a), filter_ok = nk::scan_tensor_filter_supported(s.di, a);
     int use = NK_PATH_SIMT;
     if (ix->path == NK_PATH_TENSOR || ix->path == NK_PATH_TENSOR_FILTER) {
@@ -139,7 +140,7 @@ static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uin
             return -1;
         }
         use = ix->path;
-    } else if (ix->path == NK_PATH_AUTO && Q > 8) {
+    } else if (ix->path == NK_PATH_AUTO && Q >= 5) {
         use = filter_ok ? NK_PATH_TENSOR_FILTER : tensor_ok ? NK_PATH_TENSOR : NK_PATH_SIMT;
     }
     const bool use_tensor = use != NK_PATH_SIMT;

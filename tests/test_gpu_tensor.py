@@ -155,9 +155,9 @@ def test_auto_dispatch(knn_lib, oracle_mod):
     ix = KnnIndex(128, metric="cosine")
     ix.upload(oracle_mod.fill_uniform(2000, 128, 1))
     ix.search(oracle_mod.fill_uniform(4, 128, 2), 5)
-    assert ix.last_path() == "simt"       # Q <= 8: one CUDA-core pass at the HBM roofline
+    assert ix.last_path() == "simt"       # Q <= 4: CUDA-core scan
     ix.search(oracle_mod.fill_uniform(40, 128, 2), 5)
-    assert ix.last_path() == "filter"     # Q > 8: tensor cores
+    assert ix.last_path() == "filter"     # Q >= 5: tensor cores
     ix.search(oracle_mod.fill_uniform(40, 128, 2), 500)
     assert ix.last_path() == "simt"       # k beyond the tensor paths
     ix.release()
