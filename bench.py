@@ -326,6 +326,10 @@ def main():
         ev[s][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    # snapshot the library's own counters for exactly the timed region (before any untimed continuation below)
+    scan_ms, scan_launches = ix.scan_time_ms()
+    ix.enable_timing(False)
+    launches = ix.stats()["kernel_launches"] - launches0 + (2 * args.steps if G > 1 else 0)
     clock_note = "sampled during the timed region"
     if t_wall < 0.6:
         # nvidia-smi cannot sample faster than ~100 ms: keep the identical step loop running (untimed) until the
@@ -342,9 +346,6 @@ def main():
     clocks["note"] = clock_note
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = sum(step_ms)
-    scan_ms, scan_launches = ix.scan_time_ms()
-    ix.enable_timing(False)
-    launches = ix.stats()["kernel_launches"] - launches0 + (2 * args.steps if G > 1 else 0)
     if dist is not None:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -187,9 +187,13 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
 //                then keeps everything with bound >= S_k - margin2 (it may beat the k-th once re-scored exactly), at
 //                most max_keep entries;  tau = S_k - margin2.
 // Caller guarantees every producer of cand[] has finished (barrier) and that *cnt <= 32*PER_LANE.
+//   floor_tau (margin mode): a threshold learnt elsewhere (the cross-CTA shared bound); survivors must also reach it.
+//   gcount != nullptr: `out` is a shared per-query list; the survivors are appended at atomicAdd(gcount, keep)
+//   (entries past out_len are dropped - the caller sizes the list so that cannot happen).
 template <int PER_LANE>
 __device__ __forceinline__ void warp_prune(uint64_t *cand, int *cnt, float *tau, uint32_t k, int lane, uint64_t *out,
-                                           int out_len, bool margin_mode, float margin2, int max_keep) {
+                                           int out_len, bool margin_mode, float margin2, int max_keep,
+                                           float floor_tau = -INFINITY, int *gcount = nullptr) {
     int n = *cnt;
     if (n > 32 * PER_LANE) n = 32 * PER_LANE;
     uint64_t v[PER_LANE];
@@ -212,7 +216,9 @@ __device__ __forceinline__ void warp_prune(uint64_t *cand, int *cnt, float *tau,
             for (int i = 0; i < PER_LANE; ++i) mine += v[i] >= c ? 1 : 0;
             if (__reduce_add_sync(0xffffffffu, mine) >= (int)k) prefix = c;
         }
-        if (margin_mode) {
+        if (prefix == 0ull) {
+            // fewer than k LIVE keys (empty slots are key 0): keep them all, no threshold yet
+        } else if (margin_mode) {
             new_tau = ord_to_float((uint32_t)(prefix >> 32)) - margin2;
             thr_key = (uint64_t)ord_bits(new_tau) << 32;  // lowest key with that score
             if (thr_key == 0ull) thr_key = 1ull;
@@ -220,6 +226,11 @@ __device__ __forceinline__ void warp_prune(uint64_t *cand, int *cnt, float *tau,
             new_tau = key_score(prefix);
             thr_key = prefix;
         }
+    }
+    if (margin_mode && floor_tau > new_tau) {
+        new_tau = floor_tau;
+        thr_key = (uint64_t)ord_bits(new_tau) << 32;
+        if (thr_key == 0ull) thr_key = 1ull;
     }
     // compaction: exclusive prefix of per-lane survivor counts
     int mine = 0;
@@ -234,18 +245,23 @@ __device__ __forceinline__ void warp_prune(uint64_t *cand, int *cnt, float *tau,
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     const int cap = margin_mode ? max_keep : (int)k;
     const int keep = total < cap ? total : cap;
+    int goff = 0;
+    if (gcount) {
+        if (lane == 0 && keep > 0) goff = atomicAdd(gcount, keep);
+        goff = __shfl_sync(0xffffffffu, goff, 0);
+    }
     int pos = incl - mine;
 #pragma unroll
     for (int i = 0; i < PER_LANE; ++i) {
         if (v[i] >= thr_key) {
             if (pos < keep) {
                 cand[pos] = v[i];
-                if (out && pos < out_len) out[pos] = v[i];
+                if (out && goff + pos < out_len) out[goff + pos] = v[i];
             }
             ++pos;
         }
     }
-    if (out)
+    if (out && !gcount)
         for (int j = keep + lane; j < out_len; j += 32) out[j] = 0ull;
     if (lane == 0) {
         *cnt = keep;

@@ -19,7 +19,7 @@ struct Workspace {
     uint64_t *partial = nullptr;  size_t partial_bytes = 0;  // [Q][grid][k] per-CTA sorted lists
     uint64_t *keys = nullptr;     size_t keys_bytes = 0;     // [Q][k] merged keys
     uint64_t *below = nullptr;    size_t below_bytes = 0;    // [Q] exclusion bounds of the k > NK_MAX_K passes
-    uint64_t *keys2 = nullptr;    size_t keys2_bytes = 0;    // [Q][c_out] filter-mode candidates (by upper bound)
+    uint64_t *keys2 = nullptr;    size_t keys2_bytes = 0;    // filter mode: shared thresholds gtau[] + list fills gcount[]; big-k: per-pass keys
     float *queries = nullptr;     size_t queries_bytes = 0;  // staged queries (host API)
     uint32_t *out_idx = nullptr;  size_t out_idx_bytes = 0;
     float *out_score = nullptr;   size_t out_score_bytes = 0;

@@ -10,7 +10,7 @@
 //           power-capped when HBM and the tensor pipes both run flat out) with a RIGOROUS error margin:
 //           |s_hat - s| <= c*|x|*|q|, c = 2^-10 + d*2^-22  (rounding of both operands + fp32 accumulation), so
 //           every row whose upper bound s_hat + B can still reach the running k-th best lower bound is kept.
-//           The few survivors (k + a handful) are re-scored EXACTLY in fp32 by rescore_kernel, so final
+//           The few survivors (k + a handful) are re-scored EXACTLY in fp32 by filter_finish_kernel, so final
 //           scores/indices carry no TF32 error at all.  If a margin buffer overflows (adversarial near-ties) a flag
 //           is raised ON DEVICE and the NT=3 kernels — enqueued behind, early-exiting when the flag is clear —
 //           redo the search exactly.  No host round trip.
@@ -77,7 +77,9 @@ struct Params {
     const float *qnorm;       // filter mode: |q| per query (1 for cosine), padded to a multiple of 64
     uint64_t *cand;           // [grid][QT][P]
     uint32_t qpad_off;        // row of this launch's first query inside the padded hi/lo/qnorm arrays
-    uint64_t *partial;        // [Q][grid][k_emit]
+    uint64_t *partial;        // exact: [Q][grid][k_emit] fixed slots; filter: [Q][grid*k_emit] shared append lists
+    uint32_t *gtau;           // filter: [Q] cross-CTA shared threshold (order-preserving bits, atomicMax; 0 = none yet)
+    int *gcount;              // filter: [Q] fill of the shared append lists
     int *flags;               // [0] fatal buffer overflow, [1] filter-margin overflow (-> exact fallback), [2] max |x|^2 bits
     const int *only_if;       // exact fallback: run only if *only_if != 0
     int debug;                // NK_TC_DEBUG bit 64: clock64 wait-time instrumentation of CTA 0
@@ -352,7 +354,31 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&sh.accempty[m]);
                     }
-                    if (row < p.n && cb < p.nq) {
+                    if (it < 2 && cb < p.nq) {
+                        // Flood tiles: until the first prune (after this CTA's second tile) every threshold is -inf and
+                        // EVERY (row, query) pair is buffered.  Place them directly - slot = tile-local row, no atomics,
+                        // no register select - instead of 256 x QT trips through the rare-push loop (~60 us per launch).
+                        const uint32_t slot = it * ROWS + rt;
+                        const uint32_t grow = (uint32_t)(p.row_base + row);
+#pragma unroll
+                        for (uint32_t c = 0; c < 64; ++c) {
+                            const uint32_t qi = cb + c;
+                            if (qi < p.nq) {
+                                float sc = __uint_as_float(c < 32 ? v0[c & 31] : v1[c & 31]) * mul;
+                                if (FILTER) {
+                                    const float qn = sh.qn[qi];
+                                    if (euclid) sc -= EUC_KEEP * fmaf(qn, qn, x2);
+                                    sc = fmaf(bnd, qn, sc);
+                                    if (sc != sc) sc = INFINITY;
+                                } else if (sc != sc) {
+                                    sc = -INFINITY;
+                                }
+                                my_cand[(size_t)qi * P + slot] = row < p.n ? make_key(sc, grow) : 0ull;  // 0 = empty slot
+                            }
+                        }
+                        if (rt == 0 && half == 0)
+                            for (uint32_t qi = m == 0 ? 0 : p.nq; qi < p.nq; ++qi) sh.cnt[qi] = (int)((it + 1) * ROWS);
+                    } else if (row < p.n && cb < p.nq) {
                         // Compact compare pass -> 64-bit mask of columns worth buffering (NaN passes); the rare pushes
                         // run in a small out-of-line loop so the hot code stays a few hundred instructions (a fully
                         // unrolled push per column was ~40 KB of SASS: I-cache thrash).
@@ -406,11 +432,25 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
             for (uint32_t qi = quad; qi < p.nq; qi += 4)
                 if (sh.cnt[qi] > prune_at) {
                     const float margin2 = !FILTER ? 0.0f : filter_margin2(p.metric, p.margin_c, __uint_as_float(sh.maxxx), sh.qn[qi]);
-                    warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, FILTER, margin2, prune_at);
+                    float floor_tau = -INFINITY;
+                    if (FILTER) {
+                        const uint32_t g = __ldcg(p.gtau + p.q0 + qi);
+                        if (g) floor_tau = ord_to_float(g);
+                    }
+                    warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, FILTER, margin2, prune_at, floor_tau);
                     // everything inside the margin must fit below prune_at, or the next tile could overflow the buffer
-                    if (FILTER && lane == 0 && sh.cnt[qi] >= prune_at) atomicExch(p.flags + 1, 1);
+                    if (FILTER && lane == 0 && sh.cnt[qi] >= prune_at) atomicOr(p.flags + 1, 1);
+                    // publish: this CTA's threshold is a lower bound on the true global k-th best score, so every CTA
+                    // may filter with the largest one any CTA has found
+                    if (FILTER && lane == 0 && sh.tau[qi] > -INFINITY) atomicMax(p.gtau + p.q0 + qi, ord_bits(sh.tau[qi]));
                 }
             group_sync(EPI_BAR, EPI_THREADS);
+            if (FILTER) {  // adopt the shared thresholds (one L2 read per query per tile)
+                for (uint32_t qi = tid - EPI_WARP0 * 32; qi < p.nq; qi += EPI_THREADS) {
+                    const uint32_t g = __ldcg(p.gtau + p.q0 + qi);
+                    if (g) sh.tau[qi] = fmaxf(sh.tau[qi], ord_to_float(g));
+                }
+            }
         }
     }
 
@@ -422,10 +462,21 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
         uint64_t *my_cand = p.cand + (size_t)blockIdx.x * QT * P;
         for (uint32_t qi = warp; qi < p.nq; qi += THREADS / 32) {
             const float margin2 = !FILTER ? 0.0f : filter_margin2(p.metric, p.margin_c, __uint_as_float(sh.maxxx), sh.qn[qi]);
-            warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane,
-                           p.partial + ((size_t)(p.q0 + qi) * gridDim.x + blockIdx.x) * p.k_emit, (int)p.k_emit, FILTER, margin2, (int)p.k_emit);
-            // the emitted list was cut at k_emit while rows inside the margin remained -> exact fallback
-            if (FILTER && lane == 0 && sh.cnt[qi] >= (int)p.k_emit && (int)p.k_emit > (int)p.k) atomicExch(p.flags + 1, 1);
+            if (FILTER) {
+                // survivors (inside this CTA's margin AND above the shared threshold) go to the query's shared list
+                float floor_tau = -INFINITY;
+                const uint32_t g = __ldcg(p.gtau + p.q0 + qi);
+                if (g) floor_tau = ord_to_float(g);
+                warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane,
+                               p.partial + (size_t)(p.q0 + qi) * gridDim.x * p.k_emit, (int)(gridDim.x * p.k_emit), true, margin2,
+                               (int)p.k_emit, floor_tau, p.gcount + p.q0 + qi);
+                // the list was cut at k_emit while rows inside the margin remained -> exact fallback
+                if (lane == 0 && sh.cnt[qi] >= (int)p.k_emit && (int)p.k_emit > (int)p.k) atomicOr(p.flags + 1, 2);
+                if (lane == 0 && sh.tau[qi] > -INFINITY) atomicMax(p.gtau + p.q0 + qi, ord_bits(sh.tau[qi]));
+            } else {
+                warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane,
+                               p.partial + ((size_t)(p.q0 + qi) * gridDim.x + blockIdx.x) * p.k_emit, (int)p.k_emit, false, 0.0f, (int)p.k_emit);
+            }
         }
         if (FILTER && !cosine && tid == 0) atomicMax(reinterpret_cast<unsigned int *>(p.flags + 2), sh.maxxx);
     }
@@ -438,38 +489,42 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Exact fp32 re-scoring of the filter survivors (one CTA per query).  cand[q][0..c_out) is sorted by upper bound
-// descending.  Every row whose upper bound reaches (k-th upper bound - 2*Bmax) may belong to the true top-k; they are
-// scored with the same fp32 arithmetic as the CUDA-core scan (dot / sqrt(|x|^2 |q|^2) etc.), sorted by
-// (score desc, row asc) and the best k written out.  If the candidate list is exhausted before the margin ends
-// the overflow flag is raised and the exact tensor-core kernels queued behind redo the search.
+// Filter-mode finish (one CTA per query): the query's shared list holds every row whose upper bound reached the
+// cross-CTA threshold (k plus a few dozen).  Sort it by bound; everything with bound >= (k-th bound - 2*Bmax) may belong
+// to the true top-k: those rows are re-scored EXACTLY in fp32 with the same arithmetic as the CUDA-core scan
+// (dot / sqrt(|x|^2 |q|^2) etc.), sorted by (score desc, row asc), and the best k written out.  A list longer than
+// FINISH_CAP (tiny shards with large k, or adversarial near-ties) raises the overflow flag; the exact kernels queued
+// behind redo the search.
 // ---------------------------------------------------------------------------------------------------
-constexpr int RESCORE_THREADS = 256;
-struct RescoreParams {
-    const void *rows;
-    int dtype;
+constexpr int FINISH_THREADS = 256;
+constexpr int FINISH_CAP = 4096;
+struct FinishParams {
+    const void *rows;        // fp32 corpus shard
     uint32_t dim;
     uint64_t row_base;
-    const float *queries;  // raw fp32 queries [Q x dim]
-    const uint64_t *cand;  // [Q][c_out]
-    uint32_t c_out, k;
+    const float *queries;    // raw fp32 queries [Q x dim]
+    const uint64_t *lists;   // [Q][list_cap] shared append lists (keys carry upper bounds)
+    const int *gcount;       // [Q]
+    uint32_t list_cap, k;
     int metric;
     float margin_c;
     int *flags;
-    uint64_t *out;         // [Q][k]
+    uint64_t *out;           // [Q][k]
 };
 
-__global__ void __launch_bounds__(RESCORE_THREADS) rescore_kernel(RescoreParams p) {
+__global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *sbuf = reinterpret_cast<uint64_t *>(smem_raw);           // 1024 keys
-    float *qs = reinterpret_cast<float *>(smem_raw + 1024 * 8);        // query
+    uint64_t *sb = reinterpret_cast<uint64_t *>(smem_raw);                      // FINISH_CAP bound keys
+    uint64_t *se = reinterpret_cast<uint64_t *>(smem_raw + FINISH_CAP * 8);     // FINISH_CAP exact keys
+    float *qs = reinterpret_cast<float *>(smem_raw + FINISH_CAP * 16);          // query
     __shared__ float s_qq;
     __shared__ int s_count;
     const uint32_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t *cand = p.cand + (size_t)q * p.c_out;
-    for (uint32_t j = tid; j < p.dim; j += RESCORE_THREADS) qs[j] = p.queries[(size_t)q * p.dim + j];
-    if (tid == 0) s_count = (int)p.c_out;
+    for (uint32_t j = tid; j < p.dim; j += FINISH_THREADS) qs[j] = p.queries[(size_t)q * p.dim + j];
+    int n = p.gcount[q];
+    if (tid == 0) atomicMax(p.flags + 3, n);  // diagnostics: longest shared list of this search
+    if (n > (int)p.list_cap) n = (int)p.list_cap;
     __syncthreads();
     if (warp == 0) {
         float a = 0.0f;
@@ -479,35 +534,109 @@ __global__ void __launch_bounds__(RESCORE_THREADS) rescore_kernel(RescoreParams 
         if (lane == 0) s_qq = a;
     }
     __syncthreads();
-    // margin: 2 * c * max|x| * |q|  (cosine: 2c; euclidean bound is on -dist^2: 2 * 2c|x||q|)
     const float margin2 = filter_margin2(p.metric, p.margin_c, __uint_as_float((unsigned int)p.flags[2]), sqrtf(s_qq));
-    const uint64_t kth_key = p.k <= p.c_out ? cand[p.k - 1] : 0ull;
-    const float thr = kth_key ? key_score(kth_key) - margin2 : -INFINITY;
-    for (uint32_t i = tid; i < p.c_out; i += RESCORE_THREADS) {
-        uint64_t key = cand[i];
-        if (key == 0ull || key_score(key) < thr) atomicMin(&s_count, (int)i);
+    const uint64_t *list = p.lists + (size_t)q * p.list_cap;
+    // k-th largest bound by radix select over the score bits that actually vary (8 bits per pass, smem histogram; the
+    // list is read from L2), then everything inside the margin below it is gathered for exact re-scoring.
+    __shared__ int hist[256];
+    __shared__ uint32_t s_prefix, s_red[2][FINISH_THREADS / 32];
+    __shared__ int s_krem;
+    uint32_t umax = 0u, umin = 0xffffffffu;
+    for (int i = tid; i < n; i += FINISH_THREADS) {
+        const uint32_t hi = (uint32_t)(__ldcg(list + i) >> 32);
+        umax = max(umax, hi);
+        umin = min(umin, hi);
+    }
+    umax = __reduce_max_sync(0xffffffffu, umax);
+    umin = __reduce_min_sync(0xffffffffu, umin);
+    if (lane == 0) { s_red[0][warp] = umax; s_red[1][warp] = umin; }
+    if (tid == 0) { s_count = 0; s_krem = (int)p.k; }
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < FINISH_THREADS / 32; ++w) { umax = max(umax, s_red[0][w]); umin = min(umin, s_red[1][w]); }
+    uint64_t thr_key = 1ull;  // fewer than k entries: keep them all
+    if (n >= (int)p.k) {
+        int rem = 32 - __clz(umax ^ umin);  // low bits in which the bounds differ (0: all equal)
+        if (tid == 0) s_prefix = rem >= 32 ? 0u : (umax >> rem) << rem;
+        while (rem > 0) {
+            const int w = rem < 8 ? rem : 8, shift = rem - w;
+            hist[tid] = 0;  // FINISH_THREADS == 256
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            for (int i = tid; i < n; i += FINISH_THREADS) {
+                const uint32_t hi = (uint32_t)(__ldcg(list + i) >> 32);
+                if (rem >= 32 || (hi >> rem) == (prefix >> rem)) atomicAdd(&hist[(hi >> shift) & ((1u << w) - 1u)], 1);
+            }
+            __syncthreads();
+            if (warp == 0) {  // digit holding the krem-th largest: lane l owns the 8 digits below nb - 8l, descending
+                const int krem = s_krem, nb = 1 << w;
+                int loc[8], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int dgt = nb - 1 - (lane * 8 + j);
+                    loc[j] = dgt >= 0 ? hist[dgt] : 0;
+                    sum += loc[j];
+                }
+                int incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                int c = incl - sum;
+                if (c < krem && incl >= krem) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (c + loc[j] >= krem) {
+                            s_prefix = prefix | ((uint32_t)(nb - 1 - (lane * 8 + j)) << shift);
+                            s_krem = krem - c;
+                            break;
+                        }
+                        c += loc[j];
+                    }
+                }
+            }
+            __syncthreads();
+            rem = shift;
+        }
+        __syncthreads();
+        thr_key = (uint64_t)ord_bits(ord_to_float(s_prefix) - margin2) << 32;
+        if (thr_key == 0ull) thr_key = 1ull;
+    }
+    for (int i = tid; i < n; i += FINISH_THREADS) {
+        const uint64_t key = __ldcg(list + i);
+        if (key >= thr_key) {
+            const int pos = atomicAdd(&s_count, 1);
+            if (pos < FINISH_CAP) sb[pos] = key;
+        }
     }
     __syncthreads();
-    const int count = s_count;
-    if (count == (int)p.c_out && tid == 0) atomicExch(p.flags + 1, 1);  // list exhausted while still inside the margin
+    if (s_count > FINISH_CAP) {  // thousands of rows inside the margin: adversarial near-ties -> exact fallback
+        if (tid == 0) atomicOr(p.flags + 1, 4);
+    }
+    const int count = s_count < FINISH_CAP ? s_count : FINISH_CAP;
     // exact scores
-    for (int i = warp; i < count; i += RESCORE_THREADS / 32) {
-        const uint32_t grow = key_row(cand[i]);
+    for (int i = warp; i < count; i += FINISH_THREADS / 32) {
+        const uint32_t grow = key_row(sb[i]);
         const size_t local = (size_t)(grow - (uint32_t)p.row_base);
         float d = 0.0f, xx = 0.0f;
-        if (p.dtype == NK_DTYPE_F16) {
-            const __half *x = static_cast<const __half *>(p.rows) + local * p.dim;
-            for (uint32_t j = lane; j < p.dim; j += 32) {
-                float v = __half2float(x[j]);
-                if (p.metric == NK_METRIC_EUCLIDEAN) { float t = v - qs[j]; d = fmaf(t, t, d); }
-                else { d = fmaf(v, qs[j], d); xx = fmaf(v, v, xx); }
-            }
-        } else {
-            const float *x = static_cast<const float *>(p.rows) + local * p.dim;
-            for (uint32_t j = lane; j < p.dim; j += 32) {
-                float v = __ldg(x + j);
-                if (p.metric == NK_METRIC_EUCLIDEAN) { float t = v - qs[j]; d = fmaf(t, t, d); }
-                else { d = fmaf(v, qs[j], d); xx = fmaf(v, v, xx); }
+        // fp32 rows, dim % 4 == 0, 16-byte aligned (tc_common_ok): 128-bit loads, all of a row's requests in flight
+        const float4 *x4 = reinterpret_cast<const float4 *>(static_cast<const float *>(p.rows) + local * p.dim);
+        const float4 *q4 = reinterpret_cast<const float4 *>(qs);
+#pragma unroll 8
+        for (uint32_t j = lane; j < p.dim / 4; j += 32) {
+            const float4 v = __ldg(x4 + j), u = q4[j];
+            if (p.metric == NK_METRIC_EUCLIDEAN) {
+                float t;
+                t = v.x - u.x; d = fmaf(t, t, d);
+                t = v.y - u.y; d = fmaf(t, t, d);
+                t = v.z - u.z; d = fmaf(t, t, d);
+                t = v.w - u.w; d = fmaf(t, t, d);
+            } else {
+                d = fmaf(v.x, u.x, d); xx = fmaf(v.x, v.x, xx);
+                d = fmaf(v.y, u.y, d); xx = fmaf(v.y, v.y, xx);
+                d = fmaf(v.z, u.z, d); xx = fmaf(v.z, v.z, xx);
+                d = fmaf(v.w, u.w, d); xx = fmaf(v.w, v.w, xx);
             }
         }
 #pragma unroll
@@ -516,21 +645,21 @@ __global__ void __launch_bounds__(RESCORE_THREADS) rescore_kernel(RescoreParams 
             xx += __shfl_xor_sync(0xffffffffu, xx, o);
         }
         if (lane == 0) {
-            float s = d;
-            if (p.metric == NK_METRIC_EUCLIDEAN) s = -d;
+            float sc = d;
+            if (p.metric == NK_METRIC_EUCLIDEAN) sc = -d;
             else if (p.metric == NK_METRIC_COSINE) {
                 float den = sqrtf(xx * s_qq);
-                s = den > 0.0f ? d / den : 0.0f;
+                sc = den > 0.0f ? d / den : 0.0f;
             }
-            if (s != s) s = -INFINITY;
-            sbuf[i] = make_key(s, grow);
+            if (sc != sc) sc = -INFINITY;
+            se[i] = make_key(sc, grow);
         }
     }
     int P2 = 32;
     while (P2 < count) P2 <<= 1;
-    for (int i = count + tid; i < P2; i += RESCORE_THREADS) sbuf[i] = 0ull;
-    block_bitonic_sort_desc(sbuf, P2);
-    for (uint32_t i = tid; i < p.k; i += RESCORE_THREADS) p.out[(size_t)q * p.k + i] = (int)i < count ? sbuf[i] : 0ull;
+    for (int i = count + tid; i < P2; i += FINISH_THREADS) se[i] = 0ull;
+    block_bitonic_sort_desc(se, P2);
+    for (uint32_t i = tid; i < p.k; i += FINISH_THREADS) p.out[(size_t)q * p.k + i] = (int)i < count ? se[i] : 0ull;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -586,7 +715,7 @@ bool scan_tensor_supported(const DeviceInfo &di, const ScanArgs &a) {
 }
 // filter (1xTF32 + exact rescoring) mode: all three metrics, k <= 192
 bool scan_tensor_filter_supported(const DeviceInfo &di, const ScanArgs &a) {
-    return tc_common_ok(di, a) && a.k <= 192;
+    return tc_common_ok(di, a) && a.k <= 192 && a.dim <= 32768;  // finish kernel keeps the query in shared memory
 }
 
 static int tc_debug_flags() {
@@ -615,6 +744,7 @@ static int launch_pass(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
     p.q0 = q0; p.nq = nq; p.k = a.k; p.qpad_off = q0;
     p.metric = a.metric; p.k_emit = k_emit; p.margin_c = margin_c; p.qnorm = qnorm;
     p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = only_if; p.debug = tc_debug_flags();
+    p.gtau = reinterpret_cast<uint32_t *>(ws.keys2); p.gcount = reinterpret_cast<int *>(ws.keys2) + (Qpad + QT_MAX);
     knn_scan_tc_kernel<NT, QT><<<grid, THREADS, smem, a.stream>>>(map_rows, map_qhi, map_qlo, p);
     NK_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
@@ -686,23 +816,21 @@ int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
     const uint32_t num_tiles = (a.n + ROWS - 1) / ROWS;
     uint32_t grid = (uint32_t)di.num_sms;
     if (grid > num_tiles) grid = num_tiles;
-    // per-CTA list: k + room for the rows inside the margin; merged candidate list per query
+    // per-CTA contribution: at most k + room for the rows inside the margin
     uint32_t k_emit = next_pow2(a.k + a.k / 2 + 32);
     if (k_emit < 64) k_emit = 64;
     if (k_emit > (uint32_t)(P - ROWS)) k_emit = P - ROWS;
-    uint32_t c_out = next_pow2(2 * a.k + 64);
-    if (c_out < 128) c_out = 128;
-    if (c_out > 1024) c_out = 1024;
     // 2^-10 (tf32 rounding of both operands) + d * 2^-22 (fp32 accumulation, truncating adders) + fp32 rounding of the norms
     const float margin_c = 9.765625e-4f + (float)a.dim * 2.384185791015625e-7f + 4e-6f;
 
     if (ws_reserve((void **)&ws.qaux, &ws.qaux_bytes, ((size_t)2 * Qpad * a.dim + Qpad + QT_MAX) * 4)) return -1;
     if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)grid * QT_MAX * P * 8)) return -1;
     if (ws_reserve((void **)&ws.partial, &ws.partial_bytes, (size_t)a.Q * grid * k_emit * 8)) return -1;
-    if (ws_reserve((void **)&ws.keys2, &ws.keys2_bytes, (size_t)a.Q * c_out * 8)) return -1;
+    if (ws_reserve((void **)&ws.keys2, &ws.keys2_bytes, (size_t)(Qpad + QT_MAX) * 8)) return -1;  // gtau[] + gcount[]
     float *qhi = ws.qaux, *qlo = ws.qaux + (size_t)Qpad * a.dim, *qnorm = ws.qaux + (size_t)2 * Qpad * a.dim;
 
-    NK_CUDA_OK(cudaMemsetAsync(ws.flags + 1, 0, 2 * sizeof(int), a.stream));  // [1] overflow, [2] max |x|^2
+    NK_CUDA_OK(cudaMemsetAsync(ws.flags + 1, 0, 3 * sizeof(int), a.stream));  // [1] overflow, [2] max |x|^2, [3] longest list
+    NK_CUDA_OK(cudaMemsetAsync(ws.keys2, 0, (size_t)(Qpad + QT_MAX) * 8, a.stream));  // shared thresholds + list fills
     const bool can_fallback = scan_tensor_supported(di, a);  // euclidean has no 3xTF32 twin: overflow -> error
     tc_prep_queries_kernel<<<Qpad, 256, 0, a.stream>>>(a.queries, a.Q, a.dim, a.metric == NK_METRIC_COSINE, qhi,
                                                        can_fallback ? qlo : nullptr, qnorm);
@@ -723,15 +851,15 @@ int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
         }
     }
     if (a.ev_end) NK_CUDA_OK(cudaEventRecord(a.ev_end, a.stream));
-    if (merge_keys(ws.partial, grid, k_emit, (size_t)grid * k_emit, a.Q, c_out, ws.keys2, a.stream, nullptr, k_emit)) return -1;
-    RescoreParams rp;
-    rp.rows = a.rows; rp.dtype = a.dtype; rp.dim = a.dim; rp.row_base = a.row_base; rp.queries = a.queries;
-    rp.cand = ws.keys2; rp.c_out = c_out; rp.k = a.k; rp.metric = a.metric; rp.margin_c = margin_c; rp.flags = ws.flags; rp.out = out_keys;
-    const size_t rsmem = 1024 * 8 + (size_t)a.dim * 4;
-    NK_CUDA_OK(cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));
-    rescore_kernel<<<a.Q, RESCORE_THREADS, rsmem, a.stream>>>(rp);
+    FinishParams fp;
+    fp.rows = a.rows; fp.dim = a.dim; fp.row_base = a.row_base; fp.queries = a.queries;
+    fp.lists = ws.partial; fp.gcount = reinterpret_cast<const int *>(ws.keys2) + (Qpad + QT_MAX); fp.list_cap = grid * k_emit; fp.k = a.k;
+    fp.metric = a.metric; fp.margin_c = margin_c; fp.flags = ws.flags; fp.out = out_keys;
+    const size_t fsmem = (size_t)FINISH_CAP * 16 + (size_t)a.dim * 4;
+    NK_CUDA_OK(cudaFuncSetAttribute(filter_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    filter_finish_kernel<<<a.Q, FINISH_THREADS, fsmem, a.stream>>>(fp);
     NK_CUDA_OK(cudaGetLastError());
-    if (launches) *launches += 2;
+    if (launches) ++*launches;
     tc_print_prof(a.stream, num_tiles, grid, (a.dim + BK - 1) / BK);
     // queued behind; every kernel returns at once unless flags[1] was raised on the device
     if (can_fallback) {

@@ -131,7 +131,7 @@ def test_filter_margin_overflow_falls_back_on_device(knn_lib, oracle_mod, metric
     gi, gs = ix.search(q, 10)
     flags = ix.debug_flags()
     ix.release()
-    assert flags[0] == 0 and flags[1] == 1, flags  # the margin buffers did overflow; the exact fallback answered
+    assert flags[0] == 0 and flags[1] != 0, flags  # a margin buffer / list did overflow (bit = which); the exact fallback answered
     oi, os_ = oracle_mod.knn_exact64(rows, q, 10, metric)
     check_parity(rows, q, 10, metric, gi, gs, oi, os_, swap_eps=5e-6)
 
