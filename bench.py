@@ -128,6 +128,20 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def load_tensor_peak():
+    """Dense TF32 TFLOP/s: half the bf16 figure (tf32 : bf16 = 1.1 : 2.25 PFLOP/s nominal, B200_PROFILING.md table).
+    Sustained bf16 because the scan runs inside a long, power-capped step."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d.get("bf16_tflops_sustained", d["bf16_tflops"])) / 2.0, \
+                "measured (MEASURED_PEAKS.json bf16_tflops_sustained / 2: dense TF32 runs at half the bf16 rate)"
+        except Exception:
+            pass
+    return 1590.0 / 2.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s bf16, / 2 for TF32)"
+
+
 def load_traffic(workload: str, path: str):
     """dram bytes per scan launch from the committed ncu --set full capture (profiles/traffic.json), or None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
@@ -407,6 +421,18 @@ def main():
                 "algorithmic_bytes_per_launch": algo_bytes_per_launch,
                 "avg_launch_ms": avg_launch_ms, "scan_launches_per_step": scan_kernel_launches / args.steps,
                 "scan_share_of_step": scan_ms / sum(step_ms)}
+    if used_path in ("tensor", "filter"):
+        # roofline fraction = max(bytes/t / BW, flops/t / tensor peak).  Large batches (several query
+        # blocks per corpus pass) are bound by the tensor pipes, not by HBM: report whichever bound is tighter.
+        tpeak, tpeak_src = load_tensor_peak()
+        flops_per_launch = 2.0 * Q * n_shard * dim * args.steps / scan_kernel_launches  # algorithmic: one product per (query, row, dim)
+        tflops = flops_per_launch / (avg_launch_ms / 1e3) / 1e12
+        roofline["tensor"] = {"achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak,
+                              "peak_source": tpeak_src, "algorithmic_flops_per_launch": flops_per_launch,
+                              "note": "algorithmic flops 2*Q*N*d; the exact path issues 3 TF32 products per element"}
+        if tflops / tpeak > achieved / peak:
+            roofline.update({"bound": "tensor", "achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak,
+                             "peak_source": tpeak_src, "hbm": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak}})
 
     line = {
         "metric": "kNN queries/sec", "value": value, "unit": "queries/s", "n_gpus": G, "steps": args.steps,

@@ -46,6 +46,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 
 // ---- TMA ------------------------------------------------------------------------------------------
+constexpr uint64_t CACHE_EVICT_NORMAL = 0x1000000000000000ull;
 constexpr uint64_t CACHE_EVICT_FIRST = 0x12F0000000000000ull;
 constexpr uint64_t CACHE_EVICT_LAST = 0x14F0000000000000ull;
 

@@ -70,7 +70,8 @@ template <int NT, int QT> struct Cfg {
 struct Params {
     uint32_t n, dim, nslab;
     uint64_t row_base;
-    uint32_t q0, nq, k;
+    uint32_t q0, nq, k;       // queries [q0, q0+nq) in this launch; nq <= qgroups * QT
+    uint32_t qgroups;         // 1, 2 or 4 query blocks sharing each corpus tile through L2 (grid % qgroups == 0)
     int metric;
     uint32_t k_emit;          // slots per (CTA, query) in `partial` (k for exact; k + margin room for filter)
     float margin_c;           // filter mode: c in |s_hat - s| <= c |x| |q|
@@ -160,6 +161,13 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t num_tiles = (p.n + ROWS - 1) / ROWS;
+    // Query groups: CTA b serves query block (b % G) over the tile subset (b / G).  The G sibling CTAs stream the SAME
+    // corpus tiles at the same pace, so a tile crosses HBM once and its other G-1 readers hit the 126 MB L2: large
+    // batches (Q > 128) stop being bound by re-reading the corpus once per 128 queries.
+    const uint32_t grp = blockIdx.x % p.qgroups, sub = blockIdx.x / p.qgroups, sgrid = gridDim.x / p.qgroups;
+    const uint32_t q0 = p.q0 + grp * QT, qpad_off = p.qpad_off + grp * QT;
+    const uint32_t nq = p.nq - grp * QT < (uint32_t)QT ? p.nq - grp * QT : (uint32_t)QT;
+    const uint64_t a_policy = p.qgroups > 1 ? ptx::CACHE_EVICT_NORMAL : ptx::CACHE_EVICT_FIRST;
     const bool prof = (p.debug & 64) && blockIdx.x == 0;
     long long acc_a = 0, acc_b = 0, acc_c = 0, acc_d = 0;
     const long long t_start = prof ? clock64() : 0;
@@ -180,7 +188,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
     if (tid < QT) {
         sh.tau[tid] = -INFINITY;
         sh.cnt[tid] = 0;
-        sh.qn[tid] = (FILTER && p.qnorm) ? p.qnorm[p.qpad_off + tid] : 1.0f;
+        sh.qn[tid] = (FILTER && p.qnorm) ? p.qnorm[qpad_off + tid] : 1.0f;
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -190,13 +198,13 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
     if (warp == 0) {
         // ===================================== TMA producer: corpus slabs ========================
         uint32_t g = 0;
-        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (uint32_t tile = sub; tile < num_tiles; tile += sgrid) {
             for (uint32_t j = 0; j < p.nslab; ++j, ++g) {
                 const uint32_t s = g % ASTAGES;
                 { TC_PROF_BEGIN(); ptx::mbar_wait(&sh.aempty_s[s], ((g / ASTAGES) & 1) ^ 1); TC_PROF_END(a); }
                 if (ptx::elect_one_sync()) {
                     ptx::mbar_arrive_expect_tx(&sh.afull_s[s], A_BYTES);
-                    ptx::tma_load_2d(&map_rows, &sh.afull_s[s], a_base + (size_t)s * A_BYTES, (int32_t)(j * BK), (int32_t)(tile * ROWS), ptx::CACHE_EVICT_FIRST);
+                    ptx::tma_load_2d(&map_rows, &sh.afull_s[s], a_base + (size_t)s * A_BYTES, (int32_t)(j * BK), (int32_t)(tile * ROWS), a_policy);
                 }
                 __syncwarp();
             }
@@ -205,15 +213,15 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
     } else if (warp == 3) {
         // ===================================== TMA producer: query slabs (L2-resident) ===========
         uint32_t g = 0;
-        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (uint32_t tile = sub; tile < num_tiles; tile += sgrid) {
             for (uint32_t j = 0; j < p.nslab; ++j, ++g) {
                 const uint32_t s = g % C::BSTAGES;
                 { TC_PROF_BEGIN(); ptx::mbar_wait(&sh.bempty[s], ((g / C::BSTAGES) & 1) ^ 1); TC_PROF_END(a); }
                 if (ptx::elect_one_sync()) {
                     unsigned char *st = b_base + (size_t)s * C::BST_BYTES;
                     ptx::mbar_arrive_expect_tx(&sh.bfull[s], C::BST_BYTES);
-                    ptx::tma_load_2d(&map_qhi, &sh.bfull[s], st, (int32_t)(j * BK), (int32_t)p.qpad_off, ptx::CACHE_EVICT_LAST);
-                    if (NT == 3) ptx::tma_load_2d(&map_qlo, &sh.bfull[s], st + B_BYTES, (int32_t)(j * BK), (int32_t)p.qpad_off, ptx::CACHE_EVICT_LAST);
+                    ptx::tma_load_2d(&map_qhi, &sh.bfull[s], st, (int32_t)(j * BK), (int32_t)qpad_off, ptx::CACHE_EVICT_LAST);
+                    if (NT == 3) ptx::tma_load_2d(&map_qlo, &sh.bfull[s], st + B_BYTES, (int32_t)(j * BK), (int32_t)qpad_off, ptx::CACHE_EVICT_LAST);
                 }
                 __syncwarp();
             }
@@ -225,7 +233,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
         const uint32_t idesc = ptx::make_idesc_tf32(128, QT);
         const uint32_t d = tmem + ACC_COL + m * QT;
         uint32_t g = 0, it = 0;
-        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (uint32_t tile = sub; tile < num_tiles; tile += sgrid, ++it) {
             for (uint32_t j = 0; j < p.nslab; ++j, ++g) {
                 const uint32_t s = g % C::BSTAGES, ts = g % C::TSTAGES;
                 if (j == 0) { TC_PROF_BEGIN(); ptx::mbar_wait(&sh.accempty[m], (it & 1) ^ 1); TC_PROF_END(b); }  // epilogue drained
@@ -264,7 +272,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
         const uint32_t r = m * 128 + quad * 32 + lane;  // row within the tile
         const uint32_t lane_base = (quad * 32u) << 16;
         uint32_t g = 0, it = 0;
-        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (uint32_t tile = sub; tile < num_tiles; tile += sgrid, ++it) {
             uint64_t xx2 = 0;  // two partial sums of |x|^2 (packed f32x2)
             for (uint32_t j = 0; j < p.nslab; ++j, ++g) {
                 const uint32_t s = g % ASTAGES, ts = g % C::TSTAGES;
@@ -319,7 +327,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
         const bool cosine = p.metric == NK_METRIC_COSINE, euclid = p.metric == NK_METRIC_EUCLIDEAN;
         const float bfac = p.margin_c * (euclid ? 2.0f : 1.0f);  // bound on -dist^2 = -(|x|^2+|q|^2-2x.q) is 2c|x||q|
         uint32_t it = 0;
-        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (uint32_t tile = sub; tile < num_tiles; tile += sgrid, ++it) {
 #pragma unroll 1
             for (uint32_t m = 0; m < 2; ++m) {
                 const uint32_t rt = m * 128 + quad * 32 + lane;
@@ -354,7 +362,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&sh.accempty[m]);
                     }
-                    if (it < 2 && cb < p.nq) {
+                    if (it < 2 && cb < nq) {
                         // Flood tiles: until the first prune (after this CTA's second tile) every threshold is -inf and
                         // EVERY (row, query) pair is buffered.  Place them directly - slot = tile-local row, no atomics,
                         // no register select - instead of 256 x QT trips through the rare-push loop (~60 us per launch).
@@ -363,7 +371,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
 #pragma unroll
                         for (uint32_t c = 0; c < 64; ++c) {
                             const uint32_t qi = cb + c;
-                            if (qi < p.nq) {
+                            if (qi < nq) {
                                 float sc = __uint_as_float(c < 32 ? v0[c & 31] : v1[c & 31]) * mul;
                                 if (FILTER) {
                                     const float qn = sh.qn[qi];
@@ -377,8 +385,8 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                             }
                         }
                         if (rt == 0 && half == 0)
-                            for (uint32_t qi = m == 0 ? 0 : p.nq; qi < p.nq; ++qi) sh.cnt[qi] = (int)((it + 1) * ROWS);
-                    } else if (row < p.n && cb < p.nq) {
+                            for (uint32_t qi = m == 0 ? 0 : nq; qi < nq; ++qi) sh.cnt[qi] = (int)((it + 1) * ROWS);
+                    } else if (row < p.n && cb < nq) {
                         // Compact compare pass -> 64-bit mask of columns worth buffering (NaN passes); the rare pushes
                         // run in a small out-of-line loop so the hot code stays a few hundred instructions (a fully
                         // unrolled push per column was ~40 KB of SASS: I-cache thrash).
@@ -396,7 +404,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                             pass1 |= !(s1 < sh.tau[cb + 32 + c]) ? (1u << c) : 0u;
                         }
                         uint64_t pass = (uint64_t)pass0 | ((uint64_t)pass1 << 32);
-                        if (p.nq - cb < 64) pass &= (1ull << (p.nq - cb)) - 1ull;
+                        if (nq - cb < 64) pass &= (1ull << (nq - cb)) - 1ull;
 #pragma unroll 1
                         while (pass) {
                             const uint32_t c = (uint32_t)__ffsll((long long)pass) - 1u;
@@ -429,12 +437,12 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
             // prune any buffer that could overflow during the next tile; the 4 epilogue warps prune different
             // queries concurrently with a register-resident warp selection
             group_sync(EPI_BAR, EPI_THREADS);  // every push of this tile is visible
-            for (uint32_t qi = quad; qi < p.nq; qi += 4)
+            for (uint32_t qi = quad; qi < nq; qi += 4)
                 if (sh.cnt[qi] > prune_at) {
                     const float margin2 = !FILTER ? 0.0f : filter_margin2(p.metric, p.margin_c, __uint_as_float(sh.maxxx), sh.qn[qi]);
                     float floor_tau = -INFINITY;
                     if (FILTER) {
-                        const uint32_t g = __ldcg(p.gtau + p.q0 + qi);
+                        const uint32_t g = __ldcg(p.gtau + q0 + qi);
                         if (g) floor_tau = ord_to_float(g);
                     }
                     warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, FILTER, margin2, prune_at, floor_tau);
@@ -442,12 +450,12 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                     if (FILTER && lane == 0 && sh.cnt[qi] >= prune_at) atomicOr(p.flags + 1, 1);
                     // publish: this CTA's threshold is a lower bound on the true global k-th best score, so every CTA
                     // may filter with the largest one any CTA has found
-                    if (FILTER && lane == 0 && sh.tau[qi] > -INFINITY) atomicMax(p.gtau + p.q0 + qi, ord_bits(sh.tau[qi]));
+                    if (FILTER && lane == 0 && sh.tau[qi] > -INFINITY) atomicMax(p.gtau + q0 + qi, ord_bits(sh.tau[qi]));
                 }
             group_sync(EPI_BAR, EPI_THREADS);
             if (FILTER) {  // adopt the shared thresholds (one L2 read per query per tile)
-                for (uint32_t qi = tid - EPI_WARP0 * 32; qi < p.nq; qi += EPI_THREADS) {
-                    const uint32_t g = __ldcg(p.gtau + p.q0 + qi);
+                for (uint32_t qi = tid - EPI_WARP0 * 32; qi < nq; qi += EPI_THREADS) {
+                    const uint32_t g = __ldcg(p.gtau + q0 + qi);
                     if (g) sh.tau[qi] = fmaxf(sh.tau[qi], ord_to_float(g));
                 }
             }
@@ -460,22 +468,22 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
     {
         const bool cosine = p.metric == NK_METRIC_COSINE;
         uint64_t *my_cand = p.cand + (size_t)blockIdx.x * QT * P;
-        for (uint32_t qi = warp; qi < p.nq; qi += THREADS / 32) {
+        for (uint32_t qi = warp; qi < nq; qi += THREADS / 32) {
             const float margin2 = !FILTER ? 0.0f : filter_margin2(p.metric, p.margin_c, __uint_as_float(sh.maxxx), sh.qn[qi]);
             if (FILTER) {
                 // survivors (inside this CTA's margin AND above the shared threshold) go to the query's shared list
                 float floor_tau = -INFINITY;
-                const uint32_t g = __ldcg(p.gtau + p.q0 + qi);
+                const uint32_t g = __ldcg(p.gtau + q0 + qi);
                 if (g) floor_tau = ord_to_float(g);
                 warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane,
-                               p.partial + (size_t)(p.q0 + qi) * gridDim.x * p.k_emit, (int)(gridDim.x * p.k_emit), true, margin2,
-                               (int)p.k_emit, floor_tau, p.gcount + p.q0 + qi);
+                               p.partial + (size_t)(q0 + qi) * gridDim.x * p.k_emit, (int)(gridDim.x * p.k_emit), true, margin2,
+                               (int)p.k_emit, floor_tau, p.gcount + q0 + qi);
                 // the list was cut at k_emit while rows inside the margin remained -> exact fallback
                 if (lane == 0 && sh.cnt[qi] >= (int)p.k_emit && (int)p.k_emit > (int)p.k) atomicOr(p.flags + 1, 2);
-                if (lane == 0 && sh.tau[qi] > -INFINITY) atomicMax(p.gtau + p.q0 + qi, ord_bits(sh.tau[qi]));
+                if (lane == 0 && sh.tau[qi] > -INFINITY) atomicMax(p.gtau + q0 + qi, ord_bits(sh.tau[qi]));
             } else {
                 warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane,
-                               p.partial + ((size_t)(p.q0 + qi) * gridDim.x + blockIdx.x) * p.k_emit, (int)p.k_emit, false, 0.0f, (int)p.k_emit);
+                               p.partial + ((size_t)(q0 + qi) * gridDim.x + blockIdx.x) * p.k_emit, (int)p.k_emit, false, 0.0f, (int)p.k_emit);
             }
         }
         if (FILTER && !cosine && tid == 0) atomicMax(reinterpret_cast<unsigned int *>(p.flags + 2), sh.maxxx);
@@ -727,7 +735,7 @@ static int tc_debug_flags() {
 template <int NT, int QT>
 static int launch_pass(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint32_t grid, uint32_t k_emit, float margin_c,
                        const float *qhi, const float *qlo, const float *qnorm, uint32_t Qpad, uint32_t q0, uint32_t nq,
-                       const int *only_if, uint64_t *launches, bool count_main) {
+                       const int *only_if, uint64_t *launches, bool count_main, uint32_t qgroups = 1) {
     using namespace tc;
     CUtensorMap map_rows, map_qhi, map_qlo;
     if (make_map(&map_rows, a.rows, a.n, a.dim, ROWS)) return -1;
@@ -741,7 +749,7 @@ static int launch_pass(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
     NK_CUDA_OK(cudaFuncSetAttribute(knn_scan_tc_kernel<NT, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     Params p;
     p.n = a.n; p.dim = a.dim; p.nslab = (a.dim + BK - 1) / BK; p.row_base = a.row_base;
-    p.q0 = q0; p.nq = nq; p.k = a.k; p.qpad_off = q0;
+    p.q0 = q0; p.nq = nq; p.k = a.k; p.qpad_off = q0; p.qgroups = qgroups;
     p.metric = a.metric; p.k_emit = k_emit; p.margin_c = margin_c; p.qnorm = qnorm;
     p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = only_if; p.debug = tc_debug_flags();
     p.gtau = reinterpret_cast<uint32_t *>(ws.keys2); p.gcount = reinterpret_cast<int *>(ws.keys2) + (Qpad + QT_MAX);
@@ -837,13 +845,19 @@ int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
     NK_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
     if (a.ev_begin) NK_CUDA_OK(cudaEventRecord(a.ev_begin, a.stream));
-    // 128 query columns per MMA while more than 64 queries remain (twice the queries per corpus byte streamed),
-    // a 64-column launch for the tail
+    // 128 query columns per MMA while more than 64 queries remain (twice the queries per corpus byte streamed), a
+    // 64-column launch for the tail.  More than 128 queries: 2 or 4 query blocks per launch share every corpus tile
+    // through L2 (sibling CTAs), so the corpus crosses HBM once per 256 / 512 queries.
+    uint32_t max_groups = 4;
+    if (const char *e = getenv("NK_TC_QGROUPS")) max_groups = (uint32_t)atoi(e);
     for (uint32_t q0 = 0; q0 < a.Q;) {
         const uint32_t left = a.Q - q0;
         if (left > 64) {
-            const uint32_t nq = left < 128u ? left : 128u;
-            if (launch_pass<1, 128>(di, a, ws, grid, k_emit, margin_c, qhi, nullptr, qnorm, Qpad, q0, nq, nullptr, launches, true)) return -1;
+            uint32_t groups = 1;
+            if (left > 3 * 128 && max_groups >= 4 && grid % 4 == 0 && grid >= 8) groups = 4;
+            else if (left > 128 && max_groups >= 2 && grid % 2 == 0 && grid >= 4) groups = 2;
+            const uint32_t nq = left < 128u * groups ? left : 128u * groups;
+            if (launch_pass<1, 128>(di, a, ws, grid, k_emit, margin_c, qhi, nullptr, qnorm, Qpad, q0, nq, nullptr, launches, true, groups)) return -1;
             q0 += nq;
         } else {
             if (launch_pass<1, 64>(di, a, ws, grid, k_emit, margin_c, qhi, nullptr, qnorm, Qpad, q0, left, nullptr, launches, true)) return -1;

@@ -92,7 +92,7 @@ def test_tensor_unsupported_shapes_fail_loudly(knn_lib, oracle_mod):
 # ---- filter mode: 1xTF32 prefilter with rigorous margins + exact fp32 rescoring --------------------------------
 @pytest.mark.parametrize("metric", ["cosine", "dot", "euclidean"])
 @pytest.mark.parametrize("shape", [(5000, 256, 64, 10), (3000, 128, 17, 10), (40_000, 64, 8, 100), (257, 100, 3, 10),
-                                   (60_000, 1024, 64, 10), (20_000, 768, 130, 10), (100, 32, 5, 192)])
+                                   (60_000, 1024, 64, 10), (20_000, 768, 130, 10), (100, 32, 5, 192), (30_000, 128, 520, 10), (9_000, 64, 300, 50)])
 def test_filter_parity(knn_lib, oracle_mod, metric, shape):
     n, d, Q, k = shape
     assert run_tc(oracle_mod, n, d, Q, k, metric, path="filter") == 0  # exact fp32 rescoring: no boundary swaps expected
