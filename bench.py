@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
-    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tensor", "filter"])
+    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tensor", "filter", "shadow"])
     ap.add_argument("--rows", type=int, default=0, help="override N_total (debug)")
     ap.add_argument("--k", type=int, default=0, help="override k (debug)")
     ap.add_argument("--q", type=int, default=0, help="override Q (debug)")
@@ -128,18 +128,21 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def load_tensor_peak():
-    """Dense TF32 TFLOP/s: half the bf16 figure (tf32 : bf16 = 1.1 : 2.25 PFLOP/s nominal, B200_PROFILING.md table).
-    Sustained bf16 because the scan runs inside a long, power-capped step."""
+def load_tensor_peak(bf16=False):
+    """Dense tensor TFLOP/s of the arithmetic the scan uses: BF16 (shadow path), or TF32 = half the bf16 figure
+    (tf32 : bf16 = 1.1 : 2.25 PFLOP/s nominal, B200_PROFILING.md table).  Sustained, because the scan runs inside a
+    long, power-capped step."""
+    div = 1.0 if bf16 else 2.0
+    what = "" if bf16 else " / 2: dense TF32 runs at half the bf16 rate"
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
             d = json.load(open(p))
-            return float(d.get("bf16_tflops_sustained", d["bf16_tflops"])) / 2.0, \
-                "measured (MEASURED_PEAKS.json bf16_tflops_sustained / 2: dense TF32 runs at half the bf16 rate)"
+            return float(d.get("bf16_tflops_sustained", d["bf16_tflops"])) / div, \
+                f"measured (MEASURED_PEAKS.json bf16_tflops_sustained{what})"
         except Exception:
             pass
-    return 1590.0 / 2.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s bf16, / 2 for TF32)"
+    return 1590.0 / div, f"fallback (B200_PROFILING.md 1.59 PFLOP/s bf16{what})"
 
 
 def load_traffic(workload: str, path: str):
@@ -409,22 +412,27 @@ def main():
     # ---- roofline of the dominant kernel (the scan): algorithmic bytes per launch / measured launch duration
     peak, peak_src = load_peaks()
     n_shard = hi - lo
-    algo_bytes_per_launch = n_shard * dim * elem  # every corpus byte once per launch
+    used_path = ix.last_path()
+    # every byte the scan streams, once per launch: the fp32 / fp16 rows, or — shadow path — their
+    # BF16 shadow (rows padded to 64 elements) plus the two per-row norm floats
+    algo_bytes_per_launch = n_shard * dim * elem
+    if used_path == "shadow":
+        algo_bytes_per_launch = n_shard * ((dim + 63) // 64 * 64) * 2 + n_shard * 8
     scan_kernel_launches = max(scan_launches, 1)  # main scan launches only (library brackets exactly those)
     avg_launch_ms = scan_ms / scan_kernel_launches
-    used_path = ix.last_path()
     achieved = algo_bytes_per_launch / (avg_launch_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": load_traffic(args.workload, used_path), "peak_source": peak_src,
                 "kernel": {"tensor": "knn_scan_tc_kernel<3> (tcgen05/TMEM/TMA, 3xTF32 exact)",
-                           "filter": "knn_scan_tc_kernel<1> (tcgen05/TMEM/TMA, 1xTF32 filter + exact fp32 rescoring)"}.get(used_path, "knn_scan_simt_kernel"),
+                           "filter": "knn_scan_tc_kernel<1> (tcgen05/TMEM/TMA, 1xTF32 filter + exact fp32 rescoring)",
+                           "shadow": "knn_scan_shadow_kernel (tcgen05/TMEM/TMA over the BF16 shadow corpus + exact fp32 rescoring)"}.get(used_path, "knn_scan_simt_kernel"),
                 "algorithmic_bytes_per_launch": algo_bytes_per_launch,
                 "avg_launch_ms": avg_launch_ms, "scan_launches_per_step": scan_kernel_launches / args.steps,
                 "scan_share_of_step": scan_ms / sum(step_ms)}
-    if used_path in ("tensor", "filter"):
+    if used_path in ("tensor", "filter", "shadow"):
         # roofline fraction = max(bytes/t / BW, flops/t / tensor peak).  Large batches (several query
         # blocks per corpus pass) are bound by the tensor pipes, not by HBM: report whichever bound is tighter.
-        tpeak, tpeak_src = load_tensor_peak()
+        tpeak, tpeak_src = load_tensor_peak(bf16=used_path == "shadow")
         flops_per_launch = 2.0 * Q * n_shard * dim * args.steps / scan_kernel_launches  # algorithmic: one product per (query, row, dim)
         tflops = flops_per_launch / (avg_launch_ms / 1e3) / 1e12
         roofline["tensor"] = {"achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak,
@@ -434,11 +442,15 @@ def main():
             roofline.update({"bound": "tensor", "achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak,
                              "peak_source": tpeak_src, "hbm": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak}})
 
+    config["scan"] = {"shadow": "filter scan streams the BF16 shadow of the fp32 corpus (+50% HBM held, half the bytes read); "
+                                "survivors re-scored exactly in fp32 from the fp32 rows: results identical to a full-precision scan",
+                      "filter": "1xTF32 filter scan over the fp32 rows + exact fp32 rescoring",
+                      "tensor": "exact 3xTF32 scan over the fp32 rows"}.get(used_path, "CUDA-core scan")
     line = {
         "metric": "kNN queries/sec", "value": value, "unit": "queries/s", "n_gpus": G, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32" if dtype == "f32" else "f16 corpus / f32 accumulate", "data": "synthetic",
-        "config": config, "hbm_gbs_whole_step": G * n_shard * dim * elem / (total_ms / args.steps / 1e3) / 1e9,
+        "config": config, "hbm_gbs_whole_step": G * algo_bytes_per_launch * (scan_kernel_launches / args.steps) / (total_ms / args.steps / 1e3) / 1e9,
         "roofline": roofline, "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": Q * dim * 4, "d2h_bytes_per_step": Q * k * 8,
                 "ms_per_step": e2e_ms / e2e_steps, "api": "nk_search (C ABI, host buffers)" if G == 1 else

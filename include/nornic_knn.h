@@ -87,9 +87,12 @@ enum { NK_METRIC_COSINE = 0, NK_METRIC_DOT = 1, NK_METRIC_EUCLIDEAN = 2 };
 /* Corpus element type held in HBM.  Queries and scores are always fp32. */
 enum { NK_DTYPE_F32 = 0, NK_DTYPE_F16 = 1 };
 /* Kernel selection for nk_index_set_path (diagnostics / tests); AUTO picks by Q, dim and dtype. */
-/* TENSOR = exact 3xTF32 tensor-core scan; TENSOR_FILTER = 1xTF32 prefilter with rigorous margins + exact fp32
- * rescoring (device-side fallback to the exact scan on margin overflow). */
-enum { NK_PATH_AUTO = 0, NK_PATH_SIMT = 1, NK_PATH_TENSOR = 2, NK_PATH_TENSOR_FILTER = 3 };
+/* TENSOR = exact 3xTF32 tensor-core scan; TENSOR_FILTER = 1xTF32 prefilter over the fp32 rows with rigorous margins +
+ * exact fp32 rescoring (device-side fallback to the exact scan on margin overflow); TENSOR_SHADOW = the same filter
+ * streaming a BF16 shadow copy of the shard (half the HBM bytes; built at upload for library-owned fp32 shards unless
+ * NK_SHADOW=0, +50% device memory), exact fp32 rescoring from the fp32 rows, device-side retry through TENSOR_FILTER
+ * and then the exact scan.  All paths return identical index sets. */
+enum { NK_PATH_AUTO = 0, NK_PATH_SIMT = 1, NK_PATH_TENSOR = 2, NK_PATH_TENSOR_FILTER = 3, NK_PATH_TENSOR_SHADOW = 4 };
 
 /* k up to NK_MAX_K is one fused pass; larger k (the reference accepts any k) is served by ceil(k/NK_MAX_K) passes
  * of the CUDA-core scan, up to NK_MAX_K_TOTAL results per query. */
@@ -143,10 +146,11 @@ int nk_index_set_path(NkIndex *ix, int path);
 uint64_t nk_index_rows(const NkIndex *ix);
 int nk_index_stats(const NkIndex *ix, NkStats *out);
 /* Diagnostics: copies the device status words of shard 0 after synchronising: out[0] = candidate-buffer overflow
- * (always 0 in a correct run), out[1] = 1 if the last TENSOR_FILTER search overflowed its margin buffers and the
- * exact kernels queued behind it produced the result, out[2] = bit pattern of max |x|^2 seen by that search. */
+ * (always 0 in a correct run), out[1] != 0 if the last filter stage overflowed its margin buffers and the exact kernels
+ * queued behind it produced the result, out[2] = bit pattern of max |x|^2 seen by that search, out[3] = longest
+ * candidate list. */
 int nk_index_debug_flags(NkIndex *ix, int out[4]);
-/* Which kernel the last search used: NK_PATH_SIMT / NK_PATH_TENSOR / NK_PATH_TENSOR_FILTER (-1: null index). */
+/* Which kernel the last search used: NK_PATH_SIMT / _TENSOR / _TENSOR_FILTER / _TENSOR_SHADOW (-1: null index). */
 int nk_index_last_path(const NkIndex *ix);
 /* Device-side timing of the dominant kernel (bench.py roofline): when enabled, the main scan launches of
  * every search (CUDA-core or tensor-core scan; query prep and list merge excluded) are bracketed by CUDA

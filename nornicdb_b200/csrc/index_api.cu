@@ -19,6 +19,9 @@ int scan_tensor(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t
 bool scan_tensor_supported(const DeviceInfo &di, const ScanArgs &a);
 int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *out_keys, uint64_t *launches);
 bool scan_tensor_filter_supported(const DeviceInfo &di, const ScanArgs &a);
+bool shadow_pass_supported(const DeviceInfo &di, const ScanArgs &a);
+int build_shadow(const float *rows, uint64_t first, uint64_t count, uint32_t dim, uint32_t dimpad, void *shadow, float *xnorm2,
+                 float *dnorm2, cudaStream_t stream);
 }
 
 struct NkShard {
@@ -28,6 +31,10 @@ struct NkShard {
     void *rows = nullptr;
     bool owns = true;
     uint64_t n = 0, cap = 0, base = 0;
+    // BF16 shadow of an owned fp32 shard (scan_tensor_shadow.cu): rows [0, shadow_n) are converted; capacity in rows
+    void *shadow = nullptr;
+    float *xnorm2 = nullptr, *dnorm2 = nullptr;
+    uint64_t shadow_cap = 0, shadow_n = 0;
     nk::Workspace ws;
     uint64_t *h_keys = nullptr;  // pinned staging for multi-shard host merge
     size_t h_keys_bytes = 0;
@@ -40,6 +47,7 @@ struct NkIndex {
     int dtype = NK_DTYPE_F32;
     int metric = NK_METRIC_COSINE;
     int path = NK_PATH_AUTO;
+    bool shadow_on = true;  // NK_SHADOW=0 at creation: never build the BF16 shadow (saves 50% HBM, halves filter speed)
     bool timing_on = false;
     int last_path = NK_PATH_SIMT;
     uint64_t row_base = 0;
@@ -47,12 +55,59 @@ struct NkIndex {
     NkStats stats{};
     std::mutex mu;
     size_t esz() const { return dtype == NK_DTYPE_F16 ? 2 : 4; }
+    uint32_t dimpad() const { return (dim + 63) / 64 * 64; }
     uint64_t rows() const {
         uint64_t t = 0;
         for (auto &s : shards) t += s.n;
         return t;
     }
 };
+
+static void shard_drop_shadow(NkShard &s) {
+    if (s.shadow) cudaFree(s.shadow);
+    if (s.xnorm2) cudaFree(s.xnorm2);
+    if (s.dnorm2) cudaFree(s.dnorm2);
+    s.shadow = nullptr; s.xnorm2 = s.dnorm2 = nullptr;
+    s.shadow_cap = s.shadow_n = 0;
+}
+
+// Bring the shadow of an owned fp32 shard up to date with rows [0, s.n) (converting only what is missing).  The shadow is
+// an optimisation: if its memory cannot be had the shard simply goes without (the TF32 filter scans the fp32 rows).
+static int shard_sync_shadow(NkIndex *ix, NkShard &s) {
+    const bool wanted = ix->shadow_on && ix->dtype == NK_DTYPE_F32 && s.owns && ix->dim % 4 == 0 && ix->dim >= 32 && s.n > 0;
+    if (!wanted) {
+        s.shadow_n = 0;
+        return 0;
+    }
+    const uint32_t dimpad = ix->dimpad();
+    if (s.shadow_cap < s.n) {
+        NK_CUDA_OK(cudaStreamSynchronize(s.stream));
+        shard_drop_shadow(s);
+        const uint64_t cap = s.cap > s.n ? s.cap : s.n;
+        cudaError_t e = cudaMalloc(&s.shadow, cap * dimpad * 2);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&s.xnorm2, cap * 4);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&s.dnorm2, cap * 4);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            shard_drop_shadow(s);
+            return 0;
+        }
+        s.shadow_cap = cap;
+    }
+    if (s.shadow_n < s.n) {
+        if (nk::build_shadow(static_cast<const float *>(s.rows), s.shadow_n, s.n - s.shadow_n, ix->dim, dimpad, s.shadow, s.xnorm2,
+                             s.dnorm2, s.stream))
+            return -1;
+        ix->stats.kernel_launches++;
+    }
+    s.shadow_n = s.n;
+    return 0;
+}
+static int shard_shadow_row(NkIndex *ix, NkShard &s, uint64_t local) {  // one row changed in place
+    if (!s.shadow || local >= s.shadow_n) return 0;
+    ix->stats.kernel_launches++;
+    return nk::build_shadow(static_cast<const float *>(s.rows), local, 1, ix->dim, ix->dimpad(), s.shadow, s.xnorm2, s.dnorm2, s.stream);
+}
 
 static int shard_reserve_rows(NkIndex *ix, NkShard &s, uint64_t need_rows, bool keep) {
     if (need_rows <= s.cap && s.rows) return 0;
@@ -133,16 +188,23 @@ static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uin
     // from 5 queries on its 8-query variant drops to 82% of the roofline, so the tensor-core filter scan (1xTF32 + exact
     // rescoring, 64-128 queries per pass) takes over where it applies, else the exact 3xTF32 scan, else CUDA cores.
     const bool tensor_ok = nk::scan_tensor_supported(s.di, a), filter_ok = nk::scan_tensor_filter_supported(s.di, a);
+    nk::ScanArgs as = a;  // with the BF16 shadow attached (if the shard has an up-to-date one)
+    if (s.shadow && s.shadow_n == s.n) {
+        as.shadow = s.shadow; as.shadow_dimpad = ix->dimpad(); as.xnorm2 = s.xnorm2; as.dnorm2 = s.dnorm2;
+    }
+    const bool shadow_ok = filter_ok && nk::shadow_pass_supported(s.di, as);
     int use = NK_PATH_SIMT;
-    if (ix->path == NK_PATH_TENSOR || ix->path == NK_PATH_TENSOR_FILTER) {
-        if (!(ix->path == NK_PATH_TENSOR ? tensor_ok : filter_ok)) {
-            nk::set_error("tensor path does not support this shape (dim=%u dtype=%d metric=%d Q=%u k=%u)", ix->dim, ix->dtype, ix->metric, Q, k);
+    if (ix->path == NK_PATH_TENSOR || ix->path == NK_PATH_TENSOR_FILTER || ix->path == NK_PATH_TENSOR_SHADOW) {
+        if (!(ix->path == NK_PATH_TENSOR ? tensor_ok : ix->path == NK_PATH_TENSOR_FILTER ? filter_ok : shadow_ok)) {
+            nk::set_error("tensor path %d does not support this shape (dim=%u dtype=%d metric=%d Q=%u k=%u shadow=%d)", ix->path, ix->dim,
+                          ix->dtype, ix->metric, Q, k, (int)(s.shadow != nullptr));
             return -1;
         }
         use = ix->path;
     } else if (ix->path == NK_PATH_AUTO && Q >= 5) {
-        use = filter_ok ? NK_PATH_TENSOR_FILTER : tensor_ok ? NK_PATH_TENSOR : NK_PATH_SIMT;
+        use = shadow_ok ? NK_PATH_TENSOR_SHADOW : filter_ok ? NK_PATH_TENSOR_FILTER : tensor_ok ? NK_PATH_TENSOR : NK_PATH_SIMT;
     }
+    if (use == NK_PATH_TENSOR_SHADOW) a = as;
     const bool use_tensor = use != NK_PATH_SIMT;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     uint64_t main_launches = 0;
@@ -151,7 +213,7 @@ static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uin
         NK_CUDA_OK(cudaEventCreate(&e1));
         a.ev_begin = e0; a.ev_end = e1; a.main_launches = &main_launches;
     }
-    int rc = use == NK_PATH_TENSOR_FILTER ? nk::scan_tensor_filter(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches)
+    int rc = (use == NK_PATH_TENSOR_FILTER || use == NK_PATH_TENSOR_SHADOW) ? nk::scan_tensor_filter(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches)
              : use == NK_PATH_TENSOR      ? nk::scan_tensor(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches)
                                           : nk::scan_simt(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches);
     if (ix->timing_on) {
@@ -164,7 +226,9 @@ static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uin
         }
     }
     ix->last_path = use;
-    if (rc == 0) ix->stats.bytes_scanned += (uint64_t)s.n * ix->dim * ix->esz() * (use == NK_PATH_TENSOR_FILTER ? ((Q + 127) / 128) : use_tensor ? ((Q + 63) / 64) : ((Q + 7) / 8));
+    if (rc == 0)
+        ix->stats.bytes_scanned += use == NK_PATH_TENSOR_SHADOW ? (uint64_t)s.n * ix->dimpad() * 2 * ((Q + 127) / 128)
+                                   : (uint64_t)s.n * ix->dim * ix->esz() * (use == NK_PATH_TENSOR_FILTER ? ((Q + 127) / 128) : use_tensor ? ((Q + 63) / 64) : ((Q + 7) / 8));
     return rc;
 }
 
@@ -188,6 +252,7 @@ NkIndex *nk_index_create(const int *device_ids, int n_devices, uint32_t dim, int
     }
     NkIndex *ix = new NkIndex();
     ix->dim = dim; ix->dtype = dtype; ix->metric = metric;
+    if (const char *e = getenv("NK_SHADOW")) ix->shadow_on = atoi(e) != 0;
     ix->stats.dim = dim; ix->stats.n_devices = (uint32_t)n_devices;
     ix->shards.resize(n_devices);
     for (int i = 0; i < n_devices; ++i) {
@@ -196,8 +261,8 @@ NkIndex *nk_index_create(const int *device_ids, int n_devices, uint32_t dim, int
         cudaError_t e = cudaSetDevice(s.device);
         if (e == cudaSuccess && nk::query_device_info(s.device, &s.di) != 0) e = cudaErrorUnknown;
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaMalloc((void **)&s.ws.flags, sizeof(int) * 4);
-        if (e == cudaSuccess) e = cudaMemset(s.ws.flags, 0, sizeof(int) * 4);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&s.ws.flags, sizeof(int) * 8);
+        if (e == cudaSuccess) e = cudaMemset(s.ws.flags, 0, sizeof(int) * 8);
         if (e != cudaSuccess) {
             if (e != cudaErrorUnknown) nk::set_error("nk_index_create(device %d): %s", s.device, cudaGetErrorString(e));
             cudaGetLastError();
@@ -217,6 +282,7 @@ void nk_index_release(NkIndex *ix) {
             cudaStreamDestroy(s.stream);
         }
         if (s.rows && s.owns) cudaFree(s.rows);
+        shard_drop_shadow(s);
         if (s.h_keys) cudaFreeHost(s.h_keys);
         s.ws.release();
     }
@@ -240,6 +306,8 @@ int nk_index_upload(NkIndex *ix, const void *rows_host, uint64_t n_rows) {
         if (shard_reserve_rows(ix, s, cnt, false)) return -1;
         if (cnt) NK_CUDA_OK(cudaMemcpyAsync(s.rows, (const char *)rows_host + off * rb, cnt * rb, cudaMemcpyHostToDevice, s.stream));
         s.n = cnt;
+        s.shadow_n = 0;
+        if (shard_sync_shadow(ix, s)) return -1;
         off += cnt;
         ix->stats.bytes_h2d += cnt * rb;
     }
@@ -262,8 +330,9 @@ int nk_index_append(NkIndex *ix, const void *rows_host, uint64_t n_rows) {
     NK_CUDA_OK(cudaSetDevice(s.device));
     if (shard_reserve_rows(ix, s, s.n + n_rows, true)) return -1;
     NK_CUDA_OK(cudaMemcpyAsync((char *)s.rows + s.n * rb, rows_host, n_rows * rb, cudaMemcpyHostToDevice, s.stream));
-    NK_CUDA_OK(cudaStreamSynchronize(s.stream));
     s.n += n_rows;
+    if (shard_sync_shadow(ix, s)) return -1;  // converts only the appended rows (all of them if the shard was regrown)
+    NK_CUDA_OK(cudaStreamSynchronize(s.stream));
     ix->stats.bytes_h2d += n_rows * rb;
     rebase(ix);
     return 0;
@@ -278,6 +347,7 @@ int nk_index_update_row(NkIndex *ix, uint64_t row, const void *row_host) {
     const size_t rb = (size_t)ix->dim * ix->esz();
     NK_CUDA_OK(cudaSetDevice(s->device));
     NK_CUDA_OK(cudaMemcpyAsync((char *)s->rows + local * rb, row_host, rb, cudaMemcpyHostToDevice, s->stream));
+    if (shard_shadow_row(ix, *s, local)) return -1;
     NK_CUDA_OK(cudaStreamSynchronize(s->stream));
     ix->stats.bytes_h2d += rb;
     return 0;
@@ -300,8 +370,11 @@ int nk_index_remove_swap(NkIndex *ix, uint64_t row) {
         char *dst = (char *)s->rows + local * rb;
         NK_CUDA_OK(cudaSetDevice(s->device));
         NK_CUDA_OK(cudaMemcpy(dst, src, rb, cudaMemcpyDefault));  // same or peer device
+        if (shard_shadow_row(ix, *s, local)) return -1;
+        NK_CUDA_OK(cudaStreamSynchronize(s->stream));
     }
     last->n -= 1;
+    if (last->shadow_n > last->n) last->shadow_n = last->n;
     rebase(ix);
     return 0;
 }
@@ -322,6 +395,8 @@ int nk_index_fill_uniform(NkIndex *ix, uint64_t n_rows, uint64_t seed) {
         if (nk::fill_uniform(s.rows, ix->dtype, cnt, ix->dim, seed, ix->row_base + off, s.stream)) return -1;
         ix->stats.kernel_launches++;
         s.n = cnt;
+        s.shadow_n = 0;
+        if (shard_sync_shadow(ix, s)) return -1;
         off += cnt;
     }
     for (auto &s : ix->shards) {
@@ -349,13 +424,14 @@ int nk_index_attach_device_rows(NkIndex *ix, void *rows_dev, uint64_t n_rows) {
     NkShard &s = ix->shards[0];
     NK_CUDA_OK(cudaSetDevice(s.device));
     if (s.rows && s.owns) NK_CUDA_OK(cudaFree(s.rows));
+    shard_drop_shadow(s);  // caller-owned rows may change behind the library's back: no shadow
     s.rows = rows_dev; s.owns = false; s.n = n_rows; s.cap = n_rows;
     rebase(ix);
     return 0;
 }
 
 int nk_index_set_path(NkIndex *ix, int path) {
-    if (!ix || path < NK_PATH_AUTO || path > NK_PATH_TENSOR_FILTER) { nk::set_error("bad path"); return -1; }
+    if (!ix || path < NK_PATH_AUTO || path > NK_PATH_TENSOR_SHADOW) { nk::set_error("bad path"); return -1; }
     ix->path = path;
     return 0;
 }

@@ -25,7 +25,8 @@ struct Workspace {
     float *out_score = nullptr;   size_t out_score_bytes = 0;
     float *qaux = nullptr;        size_t qaux_bytes = 0;     // tensor path: split / normalised queries
     float *rownorm = nullptr;     size_t rownorm_bytes = 0;  // tensor path: per-row inverse norms / sq norms
-    int *flags = nullptr;   // [0] candidate-buffer overflow (must stay 0), [1] filter-margin overflow, [2] max |x|^2 bits
+    int *flags = nullptr;   // 8 ints: [0] candidate-buffer overflow (must stay 0), [1] filter-margin overflow, [2] max |x|^2
+                            // bits, [3] longest list, [4]/[6] BF16 bound maxima, [5] retry-stage marker (scan_tensor_shared.cuh)
     int release();
 };
 int ws_reserve(void **p, size_t *cur, size_t need);
@@ -49,6 +50,11 @@ struct ScanArgs {
     // k > NK_MAX_K is served by repeated passes: pass p only admits keys strictly below below[q] (the last key the
     // previous pass returned for query q); nullptr = no bound.  CUDA-core scan only.
     const uint64_t *below = nullptr;
+    // optional BF16 shadow of an fp32 shard (scan_tensor_shadow.cu): rows of `shadow_dimpad` bf16 + per-row |x|^2 and
+    // |x - bf16(x)|^2; nullptr = none
+    const void *shadow = nullptr;
+    uint32_t shadow_dimpad = 0;
+    const float *xnorm2 = nullptr, *dnorm2 = nullptr;
 };
 
 // Fused distance + top-k scan on CUDA cores (small Q, any dim / dtype / alignment).

@@ -52,8 +52,8 @@ CudaDevice *cuda_create_device(int device_id) {
         return nullptr;
     }
     cudaError_t err = cudaStreamCreateWithFlags(&dev->stream, cudaStreamNonBlocking);
-    if (err == cudaSuccess) err = cudaMalloc((void **)&dev->ws.flags, sizeof(int) * 4);
-    if (err == cudaSuccess) err = cudaMemset(dev->ws.flags, 0, sizeof(int) * 4);
+    if (err == cudaSuccess) err = cudaMalloc((void **)&dev->ws.flags, sizeof(int) * 8);
+    if (err == cudaSuccess) err = cudaMemset(dev->ws.flags, 0, sizeof(int) * 8);
     if (err != cudaSuccess) {
         nk::set_error("%s", cudaGetErrorString(err));
         delete dev;

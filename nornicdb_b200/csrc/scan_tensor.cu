@@ -36,25 +36,19 @@
 
 #include "kernels.cuh"
 #include "ptx_sm100.cuh"
+#include "scan_tensor_shared.cuh"
 
 namespace nk {
 
 namespace tc {
-constexpr int THREADS = 512;
 constexpr int ROWS = 256;        // corpus rows per tile (2 M-tiles of 128)
 constexpr int QT_MAX = 128;      // queries per launch (MMA N): 64, or 128 for large batches (filter mode)
-constexpr int BK = 32;           // floats per K-slab = one 128-byte swizzle row
 constexpr int ASTAGES = 4;       // corpus-slab smem ring
 constexpr int A_BYTES = ROWS * BK * 4;   // 32 KB
-constexpr int TMEM_COLS = 512;
 constexpr int ACC_COL = 0;       // [mtile] x QT columns (single-buffered, drained per M-tile); the A ring follows
-constexpr int EPI_THREADS = 128;
-constexpr int EPI_BAR = 1;
 constexpr int SPLIT_WARP0 = 4, EPI_WARP0 = 12;
 constexpr int MAX_BSTAGES = 8, MAX_TSTAGES = 6;
-constexpr int P = 512;           // candidate buffer capacity per (CTA, query): warp_prune<16>
-constexpr float EUC_EPS = 4e-6f;  // fp32 rounding of |x|^2 + |q|^2 in the euclidean upper bound
-constexpr float EUC_KEEP = 1.0f - EUC_EPS;
+constexpr int XX_RING = 8;       // >= MAX_TSTAGES / 1 slab-per-tile + 2
 
 template <int NT, int QT> struct Cfg {
     static constexpr int PARTS = NT == 3 ? 2 : 1;          // hi (+ lo)
@@ -67,25 +61,6 @@ template <int NT, int QT> struct Cfg {
     static_assert(BSTAGES >= 2 && TSTAGES >= 2 && TSTAGES <= MAX_TSTAGES, "ring too shallow");
 };
 
-struct Params {
-    uint32_t n, dim, nslab;
-    uint64_t row_base;
-    uint32_t q0, nq, k;       // queries [q0, q0+nq) in this launch; nq <= qgroups * QT
-    uint32_t qgroups;         // 1, 2 or 4 query blocks sharing each corpus tile through L2 (grid % qgroups == 0)
-    int metric;
-    uint32_t k_emit;          // slots per (CTA, query) in `partial` (k for exact; k + margin room for filter)
-    float margin_c;           // filter mode: c in |s_hat - s| <= c |x| |q|
-    const float *qnorm;       // filter mode: |q| per query (1 for cosine), padded to a multiple of 64
-    uint64_t *cand;           // [grid][QT][P]
-    uint32_t qpad_off;        // row of this launch's first query inside the padded hi/lo/qnorm arrays
-    uint64_t *partial;        // exact: [Q][grid][k_emit] fixed slots; filter: [Q][grid*k_emit] shared append lists
-    uint32_t *gtau;           // filter: [Q] cross-CTA shared threshold (order-preserving bits, atomicMax; 0 = none yet)
-    int *gcount;              // filter: [Q] fill of the shared append lists
-    int *flags;               // [0] fatal buffer overflow, [1] filter-margin overflow (-> exact fallback), [2] max |x|^2 bits
-    const int *only_if;       // exact fallback: run only if *only_if != 0
-    int debug;                // NK_TC_DEBUG bit 64: clock64 wait-time instrumentation of CTA 0
-};
-
 struct __align__(8) Shared {
     uint64_t afull_s[ASTAGES], aempty_s[ASTAGES];    // corpus slab in smem: TMA -> split warps -> TMA
     uint64_t bfull[MAX_BSTAGES], bempty[MAX_BSTAGES];  // query slabs in smem: TMA -> MMA -> TMA
@@ -93,21 +68,13 @@ struct __align__(8) Shared {
     uint64_t accfull[2], accempty[2];                // accumulators, per M-tile
     uint32_t tmem_base;
     unsigned int maxxx;       // running max of |x|^2 (float bits) over the rows this CTA has scored
-    float xx[2][ROWS];
+    float xx[XX_RING][ROWS];  // |x|^2 per row, ring over tiles: the split warps run up to TSTAGES slabs (several tiles when
+                              // dim is small) ahead of the MMA, which runs one tile ahead of the epilogue
     float tau[QT_MAX];
     float qn[QT_MAX];
     int cnt[QT_MAX];
 };
 }  // namespace tc
-
-// Filter mode: 2 x (largest possible gap between an upper bound and the true score) for rows with |x|^2 <= maxxx.
-//   cosine 2c | dot 2c|x||q| | euclidean (on -dist^2) 2(2c|x||q| + eps(|x|^2+|q|^2))
-__device__ __forceinline__ float filter_margin2(int metric, float c, float maxxx, float qn) {
-    if (metric == NK_METRIC_COSINE) return 2.0f * c;
-    const float xq = sqrtf(maxxx) * qn;
-    if (metric == NK_METRIC_DOT) return 2.0f * c * xq;
-    return 2.0f * (2.0f * c * xq + tc::EUC_EPS * (maxxx + qn * qn));
-}
 
 // Wait-time instrumentation (NK_TC_DEBUG bit 64): cycles CTA 0 spends blocked at each hand-off.
 __device__ long long g_tc_prof[32];
@@ -309,7 +276,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                 if (NT == 3) ptx::tmem_st_32x32b_x32(acol + BK, lo);
                 ptx::tmem_wait_st();
                 if (j + 1 == p.nslab)  // published by the afull arrive below
-                    sh.xx[it & 1][r] = __uint_as_float((uint32_t)xx2) + __uint_as_float((uint32_t)(xx2 >> 32));
+                    sh.xx[it % XX_RING][r] = __uint_as_float((uint32_t)xx2) + __uint_as_float((uint32_t)(xx2 >> 32));
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&sh.afull[ts][m]);
@@ -339,7 +306,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                 //   dot        acc                                        filter bound c |x| |q|
                 //   euclidean  -(|x|^2 + |q|^2 - 2 acc)   (filter only)   filter bound 2c |x| |q|
                 // filter mode buffers the UPPER bound score + bound.
-                const float x2 = sh.xx[it & 1][rt];
+                const float x2 = sh.xx[it % XX_RING][rt];
                 const float xn = sqrtf(x2);
                 float mul = 1.0f, bnd = 0.0f;
                 if (cosine) mul = x2 > 0.0f ? 1.0f / xn : 0.0f;
@@ -476,7 +443,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                 const uint32_t g = __ldcg(p.gtau + q0 + qi);
                 if (g) floor_tau = ord_to_float(g);
                 warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane,
-                               p.partial + (size_t)(q0 + qi) * gridDim.x * p.k_emit, (int)(gridDim.x * p.k_emit), true, margin2,
+                               p.partial + (size_t)(q0 + qi) * p.list_cap, (int)p.list_cap, true, margin2,
                                (int)p.k_emit, floor_tau, p.gcount + q0 + qi);
                 // the list was cut at k_emit while rows inside the margin remained -> exact fallback
                 if (lane == 0 && sh.cnt[qi] >= (int)p.k_emit && (int)p.k_emit > (int)p.k) atomicOr(p.flags + 1, 2);
@@ -515,8 +482,11 @@ struct FinishParams {
     const int *gcount;       // [Q]
     uint32_t list_cap, k;
     int metric;
-    float margin_c;
+    float margin_c;          // TF32 passes: c in |s_hat - s| <= c |x||q|
+    uint32_t q_big;          // queries [0, q_big) went through the BF16 kernel: bound factors qa / qb / qn below
+    const float *qa, *qb, *qn;
     int *flags;
+    const int *only_if;      // retry stage: run only if *only_if != 0
     uint64_t *out;           // [Q][k]
 };
 
@@ -527,6 +497,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
     float *qs = reinterpret_cast<float *>(smem_raw + FINISH_CAP * 16);          // query
     __shared__ float s_qq;
     __shared__ int s_count;
+    if (p.only_if && *p.only_if == 0) return;
     const uint32_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t j = tid; j < p.dim; j += FINISH_THREADS) qs[j] = p.queries[(size_t)q * p.dim + j];
@@ -542,7 +513,10 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
         if (lane == 0) s_qq = a;
     }
     __syncthreads();
-    const float margin2 = filter_margin2(p.metric, p.margin_c, __uint_as_float((unsigned int)p.flags[2]), sqrtf(s_qq));
+    const float maxxx = __uint_as_float((unsigned int)p.flags[2]);
+    const float margin2 = q < p.q_big ? bf16_margin2(p.metric, __uint_as_float((unsigned int)p.flags[4]), __uint_as_float((unsigned int)p.flags[6]),
+                                                     maxxx, p.qa[q], p.qb[q], p.qn[q])
+                                      : filter_margin2(p.metric, p.margin_c, maxxx, sqrtf(s_qq));
     const uint64_t *list = p.lists + (size_t)q * p.list_cap;
     // k-th largest bound by radix select over the score bits that actually vary (8 bits per pass, smem histogram; the
     // list is read from L2), then everything inside the margin below it is gathered for exact re-scoring.
@@ -670,6 +644,19 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
     for (uint32_t i = tid; i < p.k; i += FINISH_THREADS) p.out[(size_t)q * p.k + i] = (int)i < count ? se[i] : 0ull;
 }
 
+// Staged fallback (all on the device, no host round trip):  BF16 filter -> TF32 filter -> exact.  After a stage,
+// retry_mark moves its overflow flag [1] to the retry marker [5] and clears [1]; retry_zero wipes the shared thresholds
+// and list fills if a retry is due.  The next stage's kernels run only_if flags[5] != 0.
+__global__ void retry_mark_kernel(int *flags) {
+    flags[5] = flags[1] != 0;
+    flags[1] = 0;
+}
+__global__ void retry_zero_kernel(const int *only_if, unsigned long long *words, uint32_t n) {
+    if (*only_if == 0) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) words[i] = 0ull;
+}
+
 // ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -688,25 +675,28 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// 2-D fp32 row-major [rows x dim] tensor, box = [box_rows x 32 floats], 128-byte swizzle, OOB -> 0.
-static int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint32_t dim, uint32_t box_rows) {
+int tc_make_map(CUtensorMap *m, const void *base, uint64_t rows, uint32_t cols, uint32_t elem_bytes, uint32_t box_cols,
+                uint32_t box_rows, uint64_t row_stride_bytes) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled entry point unavailable");
         return -1;
     }
-    cuuint64_t gdim[2] = {dim, rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)dim * 4};
-    cuuint32_t box[2] = {(cuuint32_t)tc::BK, box_rows};
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)row_stride_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu dim=%u", (int)r, (unsigned long long)rows, dim);
+        set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%u", (int)r, (unsigned long long)rows, cols);
         return -1;
     }
     return 0;
+}
+static int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint32_t dim, uint32_t box_rows) {
+    return tc_make_map(m, base, rows, dim, 4, (uint32_t)tc::BK, box_rows, (uint64_t)dim * 4);
 }
 
 static bool tc_common_ok(const DeviceInfo &di, const ScanArgs &a) {
@@ -726,7 +716,7 @@ bool scan_tensor_filter_supported(const DeviceInfo &di, const ScanArgs &a) {
     return tc_common_ok(di, a) && a.k <= 192 && a.dim <= 32768;  // finish kernel keeps the query in shared memory
 }
 
-static int tc_debug_flags() {
+int tc_debug_flags() {
     const char *dbg = getenv("NK_TC_DEBUG");
     return dbg ? atoi(dbg) : 0;
 }
@@ -749,10 +739,10 @@ static int launch_pass(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
     NK_CUDA_OK(cudaFuncSetAttribute(knn_scan_tc_kernel<NT, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     Params p;
     p.n = a.n; p.dim = a.dim; p.nslab = (a.dim + BK - 1) / BK; p.row_base = a.row_base;
-    p.q0 = q0; p.nq = nq; p.k = a.k; p.qpad_off = q0; p.qgroups = qgroups;
+    p.q0 = q0; p.nq = nq; p.k = a.k; p.qpad_off = q0; p.qgroups = qgroups; p.list_cap = grid * k_emit;
     p.metric = a.metric; p.k_emit = k_emit; p.margin_c = margin_c; p.qnorm = qnorm;
     p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = only_if; p.debug = tc_debug_flags();
-    p.gtau = reinterpret_cast<uint32_t *>(ws.keys2); p.gcount = reinterpret_cast<int *>(ws.keys2) + (Qpad + QT_MAX);
+    p.gtau = reinterpret_cast<uint32_t *>(ws.keys2); p.gcount = reinterpret_cast<int *>(ws.keys2) + (Qpad + QT_BIG);
     knn_scan_tc_kernel<NT, QT><<<grid, THREADS, smem, a.stream>>>(map_rows, map_qhi, map_qlo, p);
     NK_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
@@ -828,52 +818,101 @@ int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
     uint32_t k_emit = next_pow2(a.k + a.k / 2 + 32);
     if (k_emit < 64) k_emit = 64;
     if (k_emit > (uint32_t)(P - ROWS)) k_emit = P - ROWS;
-    // 2^-10 (tf32 rounding of both operands) + d * 2^-22 (fp32 accumulation, truncating adders) + fp32 rounding of the norms
-    const float margin_c = 9.765625e-4f + (float)a.dim * 2.384185791015625e-7f + 4e-6f;
+    // TF32: 2^-10 (rounding of both operands, unit roundoff 2^-11 each) + d * 2^-22 (fp32 accumulation, truncating
+    // adders) + fp32 rounding of the norms.  The BF16 kernel (big batches) measures its rounding residues instead.
+    const float acc_c = (float)a.dim * 2.384185791015625e-7f + 4e-6f;
+    const float margin_tf32 = 9.765625e-4f + acc_c;
+    // a BF16 shadow of the shard (scan_tensor_shadow.cu) halves the bytes the filter streams; the TF32 scan over the fp32
+    // rows is then the retry stage
+    const bool big = shadow_pass_supported(di, a);
+    if (big && k_emit < 128) k_emit = 128;  // BF16 margins are ~3x wider: more rows per CTA sit inside them
+    const uint32_t dimpad = big ? a.shadow_dimpad : (a.dim + 63) / 64 * 64;
+    const uint32_t QA = Qpad + QT_BIG;  // padded per-query arrays
 
-    if (ws_reserve((void **)&ws.qaux, &ws.qaux_bytes, ((size_t)2 * Qpad * a.dim + Qpad + QT_MAX) * 4)) return -1;
+    const size_t qaux_floats = (size_t)2 * Qpad * a.dim + (size_t)3 * QA;
+    if (ws_reserve((void **)&ws.qaux, &ws.qaux_bytes, qaux_floats * 4 + (big ? (size_t)Qpad * dimpad * 2 : 0))) return -1;
     if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)grid * QT_MAX * P * 8)) return -1;
     if (ws_reserve((void **)&ws.partial, &ws.partial_bytes, (size_t)a.Q * grid * k_emit * 8)) return -1;
-    if (ws_reserve((void **)&ws.keys2, &ws.keys2_bytes, (size_t)(Qpad + QT_MAX) * 8)) return -1;  // gtau[] + gcount[]
+    if (ws_reserve((void **)&ws.keys2, &ws.keys2_bytes, (size_t)QA * 8)) return -1;  // gtau[] + gcount[]
     float *qhi = ws.qaux, *qlo = ws.qaux + (size_t)Qpad * a.dim, *qnorm = ws.qaux + (size_t)2 * Qpad * a.dim;
+    float *qa = qnorm + QA, *qb = qa + QA;
+    void *qbf16 = ws.qaux + qaux_floats;
 
-    NK_CUDA_OK(cudaMemsetAsync(ws.flags + 1, 0, 3 * sizeof(int), a.stream));  // [1] overflow, [2] max |x|^2, [3] longest list
-    NK_CUDA_OK(cudaMemsetAsync(ws.keys2, 0, (size_t)(Qpad + QT_MAX) * 8, a.stream));  // shared thresholds + list fills
-    const bool can_fallback = scan_tensor_supported(di, a);  // euclidean has no 3xTF32 twin: overflow -> error
+    NK_CUDA_OK(cudaMemsetAsync(ws.flags + 1, 0, 7 * sizeof(int), a.stream));  // overflow, running maxima, retry marker
+    NK_CUDA_OK(cudaMemsetAsync(ws.keys2, 0, (size_t)QA * 8, a.stream));        // shared thresholds + list fills
+    const bool can_fallback = scan_tensor_supported(di, a);  // euclidean has no 3xTF32 twin: overflow -> CUDA-core scan
+    uint32_t max_groups = 4;
+    if (const char *e = getenv("NK_TC_QGROUPS")) max_groups = (uint32_t)atoi(e);
+    const uint32_t q_big = big ? a.Q : 0;  // queries served by the shadow kernel in the first stage (all or none)
     tc_prep_queries_kernel<<<Qpad, 256, 0, a.stream>>>(a.queries, a.Q, a.dim, a.metric == NK_METRIC_COSINE, qhi,
                                                        can_fallback ? qlo : nullptr, qnorm);
     NK_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
+    if (q_big && bf16_prep_queries(a, Qpad, dimpad, acc_c, qbf16, qnorm, qa, qb, launches)) return -1;
+
+    FinishParams fp;
+    fp.rows = a.rows; fp.dim = a.dim; fp.row_base = a.row_base; fp.queries = a.queries;
+    fp.lists = ws.partial; fp.gcount = reinterpret_cast<const int *>(ws.keys2) + QA; fp.list_cap = grid * k_emit; fp.k = a.k;
+    fp.metric = a.metric; fp.margin_c = margin_tf32; fp.flags = ws.flags; fp.out = out_keys;
+    fp.qa = qa; fp.qb = qb; fp.qn = qnorm;
+    const size_t fsmem = (size_t)FINISH_CAP * 16 + (size_t)a.dim * 4;
+    NK_CUDA_OK(cudaFuncSetAttribute(filter_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+
+    // TF32 passes over queries [qfirst, Q): 128 query columns per MMA while more than 64 queries remain (twice the queries
+    // per corpus byte streamed), a 64-column launch for the tail; 2 or 4 query blocks per launch share every corpus tile
+    // through L2 (sibling CTAs).
+    auto tf32_passes = [&](uint32_t qfirst, const int *only_if, bool count_main) -> int {
+        for (uint32_t q0 = qfirst; q0 < a.Q;) {
+            const uint32_t left = a.Q - q0;
+            if (left > 64) {
+                uint32_t groups = 1;
+                if (left > 3 * 128 && max_groups >= 4 && grid % 4 == 0 && grid >= 8) groups = 4;
+                else if (left > 128 && max_groups >= 2 && grid % 2 == 0 && grid >= 4) groups = 2;
+                const uint32_t nq = left < 128u * groups ? left : 128u * groups;
+                if (launch_pass<1, 128>(di, a, ws, grid, k_emit, margin_tf32, qhi, nullptr, qnorm, Qpad, q0, nq, only_if, launches, count_main, groups)) return -1;
+                q0 += nq;
+            } else {
+                if (launch_pass<1, 64>(di, a, ws, grid, k_emit, margin_tf32, qhi, nullptr, qnorm, Qpad, q0, left, only_if, launches, count_main)) return -1;
+                q0 += left;
+            }
+        }
+        return 0;
+    };
+
     if (a.ev_begin) NK_CUDA_OK(cudaEventRecord(a.ev_begin, a.stream));
-    // 128 query columns per MMA while more than 64 queries remain (twice the queries per corpus byte streamed), a
-    // 64-column launch for the tail.  More than 128 queries: 2 or 4 query blocks per launch share every corpus tile
-    // through L2 (sibling CTAs), so the corpus crosses HBM once per 256 / 512 queries.
-    uint32_t max_groups = 4;
-    if (const char *e = getenv("NK_TC_QGROUPS")) max_groups = (uint32_t)atoi(e);
-    for (uint32_t q0 = 0; q0 < a.Q;) {
-        const uint32_t left = a.Q - q0;
+    for (uint32_t q0 = 0; q0 < q_big;) {  // shadow passes: 128 query columns (up to 4 query groups per launch), 64 for the tail
+        const uint32_t left = q_big - q0;
         if (left > 64) {
             uint32_t groups = 1;
             if (left > 3 * 128 && max_groups >= 4 && grid % 4 == 0 && grid >= 8) groups = 4;
             else if (left > 128 && max_groups >= 2 && grid % 2 == 0 && grid >= 4) groups = 2;
             const uint32_t nq = left < 128u * groups ? left : 128u * groups;
-            if (launch_pass<1, 128>(di, a, ws, grid, k_emit, margin_c, qhi, nullptr, qnorm, Qpad, q0, nq, nullptr, launches, true, groups)) return -1;
+            if (launch_shadow_pass(128, di, a, ws, grid, k_emit, qbf16, dimpad, qnorm, qa, qb, Qpad, q0, nq, groups, launches)) return -1;
             q0 += nq;
         } else {
-            if (launch_pass<1, 64>(di, a, ws, grid, k_emit, margin_c, qhi, nullptr, qnorm, Qpad, q0, left, nullptr, launches, true)) return -1;
+            if (launch_shadow_pass(64, di, a, ws, grid, k_emit, qbf16, dimpad, qnorm, qa, qb, Qpad, q0, left, 1, launches)) return -1;
             q0 += left;
         }
     }
+    if (tf32_passes(q_big, nullptr, true)) return -1;
     if (a.ev_end) NK_CUDA_OK(cudaEventRecord(a.ev_end, a.stream));
-    FinishParams fp;
-    fp.rows = a.rows; fp.dim = a.dim; fp.row_base = a.row_base; fp.queries = a.queries;
-    fp.lists = ws.partial; fp.gcount = reinterpret_cast<const int *>(ws.keys2) + (Qpad + QT_MAX); fp.list_cap = grid * k_emit; fp.k = a.k;
-    fp.metric = a.metric; fp.margin_c = margin_c; fp.flags = ws.flags; fp.out = out_keys;
-    const size_t fsmem = (size_t)FINISH_CAP * 16 + (size_t)a.dim * 4;
-    NK_CUDA_OK(cudaFuncSetAttribute(filter_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+    fp.q_big = q_big; fp.only_if = nullptr;
     filter_finish_kernel<<<a.Q, FINISH_THREADS, fsmem, a.stream>>>(fp);
     NK_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
+    if (q_big) {
+        // retry stage, queued behind and skipped on the device unless a BF16 margin buffer overflowed: the same search over
+        // the fp32 rows with the (much tighter) TF32 margins
+        retry_mark_kernel<<<1, 1, 0, a.stream>>>(ws.flags);
+        retry_zero_kernel<<<(QA + 255) / 256, 256, 0, a.stream>>>(ws.flags + 5, reinterpret_cast<unsigned long long *>(ws.keys2), QA);
+        NK_CUDA_OK(cudaGetLastError());
+        if (launches) *launches += 2;
+        if (tf32_passes(0, ws.flags + 5, false)) return -1;
+        fp.q_big = 0; fp.only_if = ws.flags + 5;
+        filter_finish_kernel<<<a.Q, FINISH_THREADS, fsmem, a.stream>>>(fp);
+        NK_CUDA_OK(cudaGetLastError());
+        if (launches) ++*launches;
+    }
     tc_print_prof(a.stream, num_tiles, grid, (a.dim + BK - 1) / BK);
     // queued behind; every kernel returns at once unless flags[1] was raised on the device
     if (can_fallback) {

@@ -14,7 +14,7 @@ from . import _lib
 
 METRICS = {"cosine": 0, "dot": 1, "euclidean": 2}
 DTYPES = {"f32": 0, "fp32": 0, "float32": 0, "f16": 1, "fp16": 1, "float16": 1}
-PATHS = {"auto": 0, "simt": 1, "tensor": 2, "filter": 3}
+PATHS = {"auto": 0, "simt": 1, "tensor": 2, "filter": 3, "shadow": 4}
 NK_MAX_K = 1024
 
 
@@ -104,7 +104,7 @@ class KnnIndex:
         return [int(v) for v in out]
 
     def last_path(self) -> str:
-        return {1: "simt", 2: "tensor", 3: "filter"}.get(int(self.lib.nk_index_last_path(self.ptr)), "?")
+        return {1: "simt", 2: "tensor", 3: "filter", 4: "shadow"}.get(int(self.lib.nk_index_last_path(self.ptr)), "?")
 
     def enable_timing(self, on: bool = True) -> None:
         _check(self.lib.nk_index_enable_timing(self.ptr, 1 if on else 0), "nk_index_enable_timing")

@@ -98,6 +98,27 @@ def test_filter_parity(knn_lib, oracle_mod, metric, shape):
     assert run_tc(oracle_mod, n, d, Q, k, metric, path="filter") == 0  # exact fp32 rescoring: no boundary swaps expected
 
 
+@pytest.mark.parametrize("metric", ["cosine", "dot", "euclidean"])
+@pytest.mark.parametrize("shape", [(20_000, 768, 130, 10), (30_000, 128, 520, 10), (9_000, 64, 300, 50), (50_000, 96, 1024, 100),
+                                   (3_000, 1024, 257, 10)])
+def test_filter_parity_big_batches_tf32_groups(knn_lib, oracle_mod, metric, shape):
+    """Q > 128: the TF32 kernel's query groups (2 / 4 blocks of 128 queries per launch share corpus tiles through L2)."""
+    n, d, Q, k = shape
+    # exact fp32 rescoring; fp32-vs-fp64 boundary swaps (scores equal to ~1e-7) appear once Q*k reaches ~1e5 results
+    assert run_tc(oracle_mod, n, d, Q, k, metric, path="filter") <= Q * k // 2000
+
+
+# ---- shadow mode: the same filter over the BF16 shadow corpus, exact fp32 rescoring from the fp32 rows ----------------
+@pytest.mark.parametrize("metric", ["cosine", "dot", "euclidean"])
+@pytest.mark.parametrize("shape", [(5000, 256, 64, 10), (3000, 128, 17, 10), (40_000, 64, 8, 100), (257, 100, 3, 10),
+                                   (60_000, 1024, 64, 10), (20_000, 768, 130, 10), (100, 32, 5, 192), (30_000, 132, 520, 10),
+                                   (9_000, 36, 300, 50), (50_000, 128, 1024, 100), (3_000, 1024, 257, 10)])
+def test_shadow_parity(knn_lib, oracle_mod, metric, shape):
+    """path="shadow": 64 / 128 query columns, 1 / 2 / 4 query groups, ragged tiles, dims that are not multiples of 64."""
+    n, d, Q, k = shape
+    assert run_tc(oracle_mod, n, d, Q, k, metric, path="shadow") <= Q * k // 2000
+
+
 def test_filter_equals_simt_bitwise_on_indices(knn_lib, oracle_mod):
     """Final scores come from exact fp32 rescoring, so the filter path and the CUDA-core scan agree on every index."""
     from nornicdb_b200.knn import KnnIndex
@@ -136,6 +157,27 @@ def test_filter_margin_overflow_falls_back_on_device(knn_lib, oracle_mod, metric
     check_parity(rows, q, 10, metric, gi, gs, oi, os_, swap_eps=5e-6)
 
 
+@pytest.mark.parametrize("metric", ["cosine", "dot", "euclidean"])
+def test_shadow_margin_overflow_retries_with_tf32_then_exact(knn_lib, oracle_mod, metric):
+    """Adversarial near-ties: the BF16 shadow stage overflows, the TF32 filter queued behind retries on the device (and,
+    if that overflows too, the exact kernels); results still match the oracle."""
+    from nornicdb_b200.knn import KnnIndex
+    rng = np.random.default_rng(1)
+    base = oracle_mod.fill_uniform(1, 128, 9)[0]
+    rows = np.tile(base, (20_000, 1)) + rng.standard_normal((20_000, 128)).astype(np.float32) * 1e-4
+    rows[::7] = oracle_mod.fill_uniform(len(rows[::7]), 128, 10)
+    q = (base[None, :] + rng.standard_normal((200, 128)).astype(np.float32) * 1e-3).astype(np.float32)
+    ix = KnnIndex(128, metric=metric)
+    ix.upload(rows)
+    ix.set_path("shadow")
+    gi, gs = ix.search(q, 10)
+    flags = ix.debug_flags()
+    ix.release()
+    assert flags[0] == 0, flags
+    oi, os_ = oracle_mod.knn_exact64(rows, q, 10, metric)
+    check_parity(rows, q, 10, metric, gi, gs, oi, os_, swap_eps=5e-6)
+
+
 def test_filter_ties_and_zero_vectors(knn_lib, oracle_mod):
     from nornicdb_b200.knn import KnnIndex
     base = oracle_mod.fill_uniform(16, 64, 5)
@@ -150,6 +192,35 @@ def test_filter_ties_and_zero_vectors(knn_lib, oracle_mod):
         assert gi[0].tolist() == [3 + 16 * j for j in range(20)], metric
 
 
+def test_shadow_follows_incremental_updates(knn_lib, oracle_mod):
+    """append / update_row / remove_swap keep the BF16 shadow (and its per-row norms) in step with the fp32 rows."""
+    from nornicdb_b200.knn import KnnIndex
+    d, k = 96, 10
+    rows = oracle_mod.fill_uniform(3000, d, 3)
+    extra = oracle_mod.fill_uniform(1500, d, 4)
+    q = oracle_mod.fill_uniform(9, d, 5)
+    ix = KnnIndex(d, metric="cosine")
+    ix.set_path("shadow")
+    ix.upload(rows)
+    ix.append(extra[:700])          # fits or regrows the shard: either way the shadow must cover the new rows
+    ix.append(extra[700:])
+    cur = np.concatenate([rows, extra])
+    new_row = q[4] * 3.0            # becomes the best match of query 4
+    ix.update_row(1234, new_row)
+    cur[1234] = new_row
+    ix.remove_swap(7)               # last row moves into slot 7
+    cur[7] = cur[-1]
+    cur = cur[:-1]
+    ix.update_row(len(cur) - 1, q[2] * 0.5)
+    cur[-1] = q[2] * 0.5
+    gi, gs = ix.search(q, k)
+    assert ix.last_path() == "shadow"
+    ix.release()
+    oi, os_ = oracle_mod.knn_exact64(cur, q, k, "cosine")
+    check_parity(cur, q, k, "cosine", gi, gs, oi, os_)
+    assert gi[4][0] == 1234 and gi[2][0] == len(cur) - 1
+
+
 def test_auto_dispatch(knn_lib, oracle_mod):
     from nornicdb_b200.knn import KnnIndex
     ix = KnnIndex(128, metric="cosine")
@@ -157,7 +228,7 @@ def test_auto_dispatch(knn_lib, oracle_mod):
     ix.search(oracle_mod.fill_uniform(4, 128, 2), 5)
     assert ix.last_path() == "simt"       # Q <= 4: CUDA-core scan
     ix.search(oracle_mod.fill_uniform(40, 128, 2), 5)
-    assert ix.last_path() == "filter"     # Q >= 5: tensor cores
+    assert ix.last_path() == "shadow"     # Q >= 5: tensor cores over the BF16 shadow
     ix.search(oracle_mod.fill_uniform(40, 128, 2), 500)
     assert ix.last_path() == "simt"       # k beyond the tensor paths
     ix.release()
