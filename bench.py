@@ -483,9 +483,11 @@ def main():
             torch.cuda.synchronize()
             ms2 = a0.elapsed_time(a1) / steps2
             sm2, sl2 = ix2.scan_time_ms()
+            p2 = ix2.last_path()
+            bytes2 = n2 * ((d2 + 63) // 64 * 64) * 2 + n2 * 8 if p2 == "shadow" else n2 * d2 * 4  # what the scan streams
             line["also"] = {"c2": {"workload": desc2, "value": Q2 / (ms2 / 1e3), "unit": "queries/s", "ms_per_step": ms2,
-                                   "steps": steps2, "scan_kernel_ms": sm2 / max(sl2, 1),
-                                   "roofline_frac": n2 * d2 * 4 / (sm2 / max(sl2, 1) / 1e3) / 1e9 / peak, "path": ix2.last_path()}}
+                                   "steps": steps2, "scan_kernel_ms": sm2 / max(sl2, 1), "algorithmic_bytes_per_launch": bytes2,
+                                   "roofline_frac": bytes2 / (sm2 / max(sl2, 1) / 1e3) / 1e9 / peak, "path": p2}}
             ix2.release()
             del q2
         except Exception as e:  # never let the secondary measurement break the contract line

@@ -183,10 +183,11 @@ static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uin
     nk::ScanArgs a;
     a.rows = s.rows; a.dtype = ix->dtype; a.n = (uint32_t)s.n; a.dim = ix->dim; a.row_base = s.base;
     a.queries = q_dev; a.Q = Q; a.k = k; a.metric = ix->metric; a.stream = stream;
-    // AUTO (measured, N=10M d=1024, ms per batch: CUDA-core 5.9 / 6.2 / 6.1 / 7.6 at Q = 1 / 2 / 4 / 8, tensor filter 5.8-5.9
-    // for any Q <= 64): the CUDA-core scan keeps Q <= 4 (no prep / rescoring kernels, lowest latency on small corpora);
-    // from 5 queries on its 8-query variant drops to 82% of the roofline, so the tensor-core filter scan (1xTF32 + exact
-    // rescoring, 64-128 queries per pass) takes over where it applies, else the exact 3xTF32 scan, else CUDA cores.
+    // AUTO (measured on B200, N=10M d=1024, ms per batch).  fp32 rows: CUDA-core scan 5.9 / 6.2 / 6.1 / 7.6 at Q = 1 / 2 /
+    // 4 / 8, TF32 tensor filter 5.8 for any Q <= 64 -> CUDA cores keep Q <= 4, tensor cores from 5 queries on.  With a
+    // BF16 shadow the filter streams half the bytes: 2.9-3.1 ms for any Q <= 128, so it serves every batch size once the
+    // shard is large enough for bytes (not launches) to matter; small shards keep the single-kernel CUDA-core scan at
+    // Q <= 4 (N=100k d=128: 86 us vs 89 us).
     const bool tensor_ok = nk::scan_tensor_supported(s.di, a), filter_ok = nk::scan_tensor_filter_supported(s.di, a);
     nk::ScanArgs as = a;  // with the BF16 shadow attached (if the shard has an up-to-date one)
     if (s.shadow && s.shadow_n == s.n) {
@@ -201,8 +202,10 @@ static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uin
             return -1;
         }
         use = ix->path;
-    } else if (ix->path == NK_PATH_AUTO && Q >= 5) {
-        use = shadow_ok ? NK_PATH_TENSOR_SHADOW : filter_ok ? NK_PATH_TENSOR_FILTER : tensor_ok ? NK_PATH_TENSOR : NK_PATH_SIMT;
+    } else if (ix->path == NK_PATH_AUTO) {
+        const bool big_shard = (uint64_t)s.n * ix->dim * 4 >= (64ull << 20);
+        if (Q >= 5) use = shadow_ok ? NK_PATH_TENSOR_SHADOW : filter_ok ? NK_PATH_TENSOR_FILTER : tensor_ok ? NK_PATH_TENSOR : NK_PATH_SIMT;
+        else if (shadow_ok && big_shard) use = NK_PATH_TENSOR_SHADOW;
     }
     if (use == NK_PATH_TENSOR_SHADOW) a = as;
     const bool use_tensor = use != NK_PATH_SIMT;

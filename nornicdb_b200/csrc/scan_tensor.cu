@@ -843,6 +843,10 @@ int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
     const bool can_fallback = scan_tensor_supported(di, a);  // euclidean has no 3xTF32 twin: overflow -> CUDA-core scan
     uint32_t max_groups = 4;
     if (const char *e = getenv("NK_TC_QGROUPS")) max_groups = (uint32_t)atoi(e);
+    // G query groups leave each CTA 1/G of the grid for its queries, i.e. G times the rows — and G times the rows inside
+    // the BF16 margin — per (CTA, query) buffer: large k keeps fewer groups so that k + margin rows stay inside k_emit
+    uint32_t max_groups_shadow = a.k <= 32 ? 4u : a.k <= 64 ? 2u : 1u;
+    if (max_groups_shadow > max_groups) max_groups_shadow = max_groups;
     const uint32_t q_big = big ? a.Q : 0;  // queries served by the shadow kernel in the first stage (all or none)
     tc_prep_queries_kernel<<<Qpad, 256, 0, a.stream>>>(a.queries, a.Q, a.dim, a.metric == NK_METRIC_COSINE, qhi,
                                                        can_fallback ? qlo : nullptr, qnorm);
@@ -884,8 +888,8 @@ int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
         const uint32_t left = q_big - q0;
         if (left > 64) {
             uint32_t groups = 1;
-            if (left > 3 * 128 && max_groups >= 4 && grid % 4 == 0 && grid >= 8) groups = 4;
-            else if (left > 128 && max_groups >= 2 && grid % 2 == 0 && grid >= 4) groups = 2;
+            if (left > 3 * 128 && max_groups_shadow >= 4 && grid % 4 == 0 && grid >= 8) groups = 4;
+            else if (left > 128 && max_groups_shadow >= 2 && grid % 2 == 0 && grid >= 4) groups = 2;
             const uint32_t nq = left < 128u * groups ? left : 128u * groups;
             if (launch_shadow_pass(128, di, a, ws, grid, k_emit, qbf16, dimpad, qnorm, qa, qb, Qpad, q0, nq, groups, launches)) return -1;
             q0 += nq;

@@ -84,24 +84,43 @@ def ncu_summary(rep, md_path, title, algorithmic_bytes=None):
 
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
-    launches(os.path.join(G, f"launches_{tag}_headline.csv"), os.path.join(OUT, f"launches_{tag}_headline.md"),
-             f"Launch list, round {tag[1:]}: bench.py headline (N=10M d=1024 Q=64 k=10 cosine), tensor-core filter path")
-    if os.path.exists(os.path.join(G, f"launches_{tag}_c2_filter.csv")):
-        launches(os.path.join(G, f"launches_{tag}_c2_filter.csv"), os.path.join(OUT, f"launches_{tag}_c2_filter.md"),
-                 f"Launch list, round {tag[1:]}: bench.py c2 (N=1M d=1024 Q=64 k=10 cosine), tensor-core filter path")
-    if os.path.exists(os.path.join(G, f"launches_{tag}_simt.csv")):
-        launches(os.path.join(G, f"launches_{tag}_simt.csv"), os.path.join(OUT, f"launches_{tag}_c2_simt.md"),
-                 f"Launch list, round {tag[1:]}: bench.py c2 (N=1M d=1024 Q=64 k=10 cosine), CUDA-core path (first working version)")
-    t = {}
-    t["headline:filter"] = ncu_summary(os.path.join(G, f"prof_{tag}_tc_headline.ncu-rep"), os.path.join(OUT, f"ncu_{tag}_scan_tc_filter_headline.md"),
-                                       "knn_scan_tc_kernel<1,64> (1xTF32 filter) — N=10M d=1024 fp32 Q=64 k=10 cosine", 10_000_000 * 1024 * 4)
-    if os.path.exists(os.path.join(G, f"prof_{tag}_tc3_headline.ncu-rep")):
-        t["headline:tensor"] = ncu_summary(os.path.join(G, f"prof_{tag}_tc3_headline.ncu-rep"), os.path.join(OUT, f"ncu_{tag}_scan_tc_exact_headline.md"),
-                                           "knn_scan_tc_kernel<3,64> (3xTF32 exact) — N=10M d=1024 fp32 Q=64 k=10 cosine", 10_000_000 * 1024 * 4)
-    t["q1:simt"] = ncu_summary(os.path.join(G, f"prof_{tag}_simt_q1.ncu-rep"), os.path.join(OUT, f"ncu_{tag}_scan_simt_q1.md"),
-                               "knn_scan_simt_kernel — N=10M d=1024 fp32 Q=1 k=10 cosine", 10_000_000 * 1024 * 4)
-    t["c4:simt"] = ncu_summary(os.path.join(G, f"prof_{tag}_simt_c4.ncu-rep"), os.path.join(OUT, f"ncu_{tag}_scan_simt_c4.md"),
-                               "knn_scan_simt_kernel — N=10M d=768 fp16 Q=1 k=10 L2", 10_000_000 * 768 * 2)
-    t["headline:simt"] = t["q1:simt"]  # same kernel, same bytes per launch (one launch = one 8-query group)
-    json.dump(t, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
+    # (csv in gpurun_out, md in profiles, title): regenerated only when the raw file is present
+    LAUNCH_LISTS = [
+        (f"launches_{tag}_headline.csv", f"launches_{tag}_headline.md",
+         f"Launch list, round {tag[1:]}: bench.py headline (N=10M d=1024 Q=64 k=10 cosine), default path (BF16 shadow filter)"),
+        (f"launches_{tag}_c2_shadow.csv", f"launches_{tag}_c2_shadow.md",
+         f"Launch list, round {tag[1:]}: bench.py c2 (N=1M d=1024 Q=64 k=10 cosine), default path (BF16 shadow filter)"),
+        (f"launches_{tag}_c3_shadow.csv", f"launches_{tag}_c3_shadow.md",
+         f"Launch list, round {tag[1:]}: bench.py c3 (N=10M d=1024 Q=1024 k=100 inner product), default path (BF16 shadow filter)"),
+        (f"launches_{tag}_c2_filter.csv", f"launches_{tag}_c2_filter.md",
+         f"Launch list, round {tag[1:]}: bench.py c2 --path filter (TF32 filter over the fp32 rows)"),
+        (f"launches_{tag}_simt.csv", f"launches_{tag}_c2_simt.md",
+         f"Launch list, round {tag[1:]}: bench.py c2 (N=1M d=1024 Q=64 k=10 cosine), CUDA-core path (first working version)"),
+    ]
+    for src, dst, title in LAUNCH_LISTS:
+        if os.path.exists(os.path.join(G, src)):
+            launches(os.path.join(G, src), os.path.join(OUT, dst), title)
+    N10, D = 10_000_000, 1024
+    CAPTURES = [  # (ncu-rep, md, title, algorithmic bytes per launch, traffic.json keys)
+        (f"prof_{tag}_shadow_headline.ncu-rep", f"ncu_{tag}_scan_shadow_headline.md",
+         "knn_scan_shadow_kernel<64> (BF16 shadow filter) — N=10M d=1024 fp32 Q=64 k=10 cosine", N10 * D * 2 + N10 * 8, ["headline:shadow"]),
+        (f"prof_{tag}_shadow_q1.ncu-rep", f"ncu_{tag}_scan_shadow_q1.md",
+         "knn_scan_shadow_kernel<64> (BF16 shadow filter) — N=10M d=1024 fp32 Q=1 k=10 cosine", N10 * D * 2 + N10 * 8, ["q1:shadow"]),
+        (f"prof_{tag}_tc_headline.ncu-rep", f"ncu_{tag}_scan_tc_filter_headline.md",
+         "knn_scan_tc_kernel<1,64> (1xTF32 filter over the fp32 rows) — N=10M d=1024 fp32 Q=64 k=10 cosine", N10 * D * 4, ["headline:filter"]),
+        (f"prof_{tag}_tc3_headline.ncu-rep", f"ncu_{tag}_scan_tc_exact_headline.md",
+         "knn_scan_tc_kernel<3,64> (3xTF32 exact) — N=10M d=1024 fp32 Q=64 k=10 cosine", N10 * D * 4, ["headline:tensor"]),
+        (f"prof_{tag}_simt_q1.ncu-rep", f"ncu_{tag}_scan_simt_q1.md",
+         "knn_scan_simt_kernel — N=10M d=1024 fp32 Q=1 k=10 cosine", N10 * D * 4, ["q1:simt", "headline:simt"]),
+        (f"prof_{tag}_simt_c4.ncu-rep", f"ncu_{tag}_scan_simt_c4.md",
+         "knn_scan_simt_kernel — N=10M d=768 fp16 Q=1 k=10 L2", N10 * 768 * 2, ["c4:simt"]),
+    ]
+    tpath = os.path.join(OUT, "traffic.json")
+    t = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    for rep, md, title, algo, keys in CAPTURES:
+        if os.path.exists(os.path.join(G, rep)):
+            v = ncu_summary(os.path.join(G, rep), os.path.join(OUT, md), title, algo)
+            for k in keys:
+                t[k] = v
+    json.dump(t, open(tpath, "w"), indent=1)
     print(json.dumps(t, indent=1))

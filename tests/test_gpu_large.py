@@ -35,14 +35,14 @@ def test_config2_full_size_against_oracle(knn_lib, oracle_mod):
     q = oracle_mod.fill_uniform(Q, d, 1337)
     oi, os_ = oracle_mod.knn_exact64(rows, q, k, "cosine")
     swaps = {}
-    for path in ("filter", "tensor", "simt"):
+    for path in ("shadow", "filter", "tensor", "simt"):
         ix.set_path(path)
         gi, gs = ix.search(q, k)
         assert ix.last_path() == path
         swaps[path] = check_parity(rows, q, k, "cosine", gi, gs, oi, os_)
     assert ix.debug_flags()[0] == 0
     ix.release()
-    assert swaps["filter"] == 0 and swaps["simt"] == 0 and swaps["tensor"] <= 2, swaps
+    assert swaps["shadow"] == 0 and swaps["filter"] == 0 and swaps["simt"] == 0 and swaps["tensor"] <= 2, swaps
 
 
 @pytest.mark.parametrize("metric,k", [("cosine", 10), ("dot", 100)])
@@ -60,9 +60,14 @@ def test_10m_rows_properties(knn_lib, oracle_mod, metric, k):
         v = (q[j] * 1.5).astype(np.float32)
         ix.update_row(row, v)
         planted[j] = row
+    ix.set_path("shadow")
+    hi, hs = ix.search(q, k)
+    assert ix.debug_flags()[:2] == [0, 0]   # no retry stage was needed
     ix.set_path("filter")
     fi, fs = ix.search(q, k)
     assert ix.debug_flags()[:2] == [0, 0]
+    # BF16-shadow filter and TF32 filter re-score the same survivors exactly: bit-identical results
+    assert (hi == fi).all() and (hs == fs).all()
     ix.set_path("simt")
     si, ss = ix.search(q[:8], k)
     _basic_properties(fi, fs, metric)
