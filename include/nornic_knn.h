@@ -147,8 +147,8 @@ uint64_t nk_index_rows(const NkIndex *ix);
 int nk_index_stats(const NkIndex *ix, NkStats *out);
 /* Diagnostics: copies the device status words of shard 0 after synchronising: out[0] = candidate-buffer overflow
  * (always 0 in a correct run), out[1] != 0 if the last filter stage overflowed its margin buffers and the exact kernels
- * queued behind it produced the result, out[2] = bit pattern of max |x|^2 seen by that search, out[3] = longest
- * candidate list. */
+ * queued behind it produced the result, out[2] = bit pattern of max |x|^2 seen by that search, out[3] = 1 if the BF16
+ * shadow stage overflowed and the TF32 filter over the fp32 rows re-ran the search. */
 int nk_index_debug_flags(NkIndex *ix, int out[4]);
 /* Which kernel the last search used: NK_PATH_SIMT / _TENSOR / _TENSOR_FILTER / _TENSOR_SHADOW (-1: null index). */
 int nk_index_last_path(const NkIndex *ix);
@@ -191,6 +191,18 @@ int nk_merge_keys_device(int device_id, const uint64_t *keys_dev, uint32_t n_lis
  * out arrays have length min(k, n_rows_subset) per query; returns that length or -1. */
 int nk_score_subset(NkIndex *ix, const float *query_host, const uint32_t *rows_host, uint32_t n_subset, uint32_t k,
                     uint32_t *out_idx, float *out_score);
+
+/* k-means routing on device (pkg/gpu/kmeans.go) for fp32 indexes.
+ * nk_index_assign_nearest = assignToCentroids (kmeans.go:458-489, metric NK_METRIC_EUCLIDEAN: nearest by squared
+ * distance) / assignToCentroidsGPU (kmeans.go:491-546, NK_METRIC_COSINE: highest cosine): the fused scan with the roles
+ * swapped — the K centroids (host, [K x dim]) are the corpus, the index's rows are the queries, read in place.
+ * assign_io (host, [rows], int32) holds the previous assignment on entry (any value, e.g. 0 as in Go) and the new one
+ * on return; *changed (nullable) = how many differ.  Ties go to the lowest centroid index.
+ * nk_index_cluster_means = updateCentroidsWithBuffer (kmeans.go:585-618): centroids_io (host, [K x dim]) <- float32 of the
+ * float64 mean of each cluster's rows; clusters without members keep their value; counts_out (nullable, [K]). */
+int nk_index_assign_nearest(NkIndex *ix, const float *centroids_host, uint32_t K, int metric, int32_t *assign_io,
+                            uint64_t *changed);
+int nk_index_cluster_means(NkIndex *ix, const int32_t *assign_host, uint32_t K, float *centroids_io, uint32_t *counts_out);
 
 /* Synthetic fp32 query block from the shared generator, on the device of a single-device index. */
 int nk_fill_uniform_device(int device_id, float *out_dev, uint64_t n_rows, uint32_t dim, uint64_t seed,

@@ -453,7 +453,9 @@ int nk_index_debug_flags(NkIndex *ix, int out[4]) {
     NkShard &s = ix->shards[0];
     NK_CUDA_OK(cudaSetDevice(s.device));
     NK_CUDA_OK(cudaDeviceSynchronize());
-    NK_CUDA_OK(cudaMemcpy(out, s.ws.flags, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    int h[8];
+    NK_CUDA_OK(cudaMemcpy(h, s.ws.flags, 8 * sizeof(int), cudaMemcpyDeviceToHost));
+    out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; out[3] = h[5];
     return 0;
 }
 
@@ -730,6 +732,108 @@ int nk_score_subset(NkIndex *ix, const float *query_host, const uint32_t *rows_h
     // order of ScoreSubset's input list)
     for (uint32_t i = 0; i < ke; ++i) out_idx[i] = pos[i] < n_subset ? rows_host[pos[i]] : 0xffffffffu;
     return (int)ke;
+}
+
+// ---- k-means routing on device (pkg/gpu/kmeans.go) -----------------------------------------------
+// Assignment is the fused scan with the roles swapped: the K centroids are the indexed corpus, the shard's rows are the
+// queries — read in place from HBM, 1024 at a time — and k = 1.  Ties go to the lowest centroid index (strict < / >
+// in kmeans.go:470-476,529-534).
+int nk_index_assign_nearest(NkIndex *ix, const float *centroids_host, uint32_t K, int metric, int32_t *assign_io, uint64_t *changed) {
+    if (!ix || !centroids_host || !assign_io) { nk::set_error("null argument"); return -1; }
+    if (ix->dtype != NK_DTYPE_F32) { nk::set_error("nk_index_assign_nearest: fp32 index required"); return -1; }
+    if (K == 0) { nk::set_error("nk_index_assign_nearest: K must be >= 1"); return -1; }
+    if (metric < NK_METRIC_COSINE || metric > NK_METRIC_EUCLIDEAN) { nk::set_error("unknown metric %d", metric); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    uint64_t total_changed = 0, off = 0;
+    for (auto &s : ix->shards) {
+        if (s.n == 0) continue;
+        NK_CUDA_OK(cudaSetDevice(s.device));
+        NkIndex *cx = nk_index_create(&s.device, 1, ix->dim, NK_DTYPE_F32, metric);
+        if (!cx) return -1;
+        uint32_t *d_idx = nullptr;
+        float *d_sc = nullptr;
+        int32_t *d_prev = nullptr;
+        unsigned long long *d_changed = nullptr, h_changed = 0;
+        int rc = nk_index_upload(cx, centroids_host, K);
+        cudaError_t e = cudaSuccess;
+        if (rc == 0) {
+            e = cudaMalloc((void **)&d_idx, s.n * 4);
+            if (e == cudaSuccess) e = cudaMalloc((void **)&d_sc, s.n * 4);
+            if (e == cudaSuccess) e = cudaMalloc((void **)&d_prev, s.n * 4);
+            if (e == cudaSuccess) e = cudaMalloc((void **)&d_changed, 8);
+            if (e == cudaSuccess) e = cudaMemsetAsync(d_changed, 0, 8, s.stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d_prev, assign_io + off, s.n * 4, cudaMemcpyHostToDevice, s.stream);
+            if (e != cudaSuccess) rc = -1;
+        }
+        const uint64_t B = 1024;
+        for (uint64_t b = 0; rc == 0 && b < s.n; b += B) {
+            const uint32_t nb = (uint32_t)std::min<uint64_t>(B, s.n - b);
+            if (nk_search_device(cx, static_cast<const float *>(s.rows) + b * ix->dim, nb, 1, d_idx + b, d_sc + b, s.stream) < 0) rc = -1;
+        }
+        if (rc == 0 && nk::count_changed(d_prev, d_idx, s.n, d_changed, s.stream)) rc = -1;
+        if (rc == 0) {
+            e = cudaMemcpyAsync(assign_io + off, d_idx, s.n * 4, cudaMemcpyDeviceToHost, s.stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&h_changed, d_changed, 8, cudaMemcpyDeviceToHost, s.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+            if (e != cudaSuccess) rc = -1;
+        }
+        if (e != cudaSuccess) { nk::set_error("nk_index_assign_nearest: %s", cudaGetErrorString(e)); cudaGetLastError(); }
+        cudaStreamSynchronize(s.stream);
+        cudaFree(d_idx); cudaFree(d_sc); cudaFree(d_prev); cudaFree(d_changed);
+        ix->stats.kernel_launches += cx->stats.kernel_launches + 1;
+        nk_index_release(cx);
+        if (rc != 0) return -1;
+        total_changed += h_changed;
+        off += s.n;
+    }
+    if (changed) *changed = total_changed;
+    return 0;
+}
+
+// Update step (kmeans.go:585-618): centroid c <- float32(mean in float64 of the rows assigned to c); clusters without
+// members keep their previous position.  Rows with an assignment outside [0, K) are ignored.
+int nk_index_cluster_means(NkIndex *ix, const int32_t *assign_host, uint32_t K, float *centroids_io, uint32_t *counts_out) {
+    if (!ix || !assign_host || !centroids_io) { nk::set_error("null argument"); return -1; }
+    if (ix->dtype != NK_DTYPE_F32) { nk::set_error("nk_index_cluster_means: fp32 index required"); return -1; }
+    if (K == 0) return 0;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    const size_t KD = (size_t)K * ix->dim;
+    std::vector<double> sums(KD, 0.0), part(KD);
+    std::vector<unsigned long long> counts(K, 0ull), cpart(K);
+    uint64_t off = 0;
+    for (auto &s : ix->shards) {
+        if (s.n == 0) continue;
+        NK_CUDA_OK(cudaSetDevice(s.device));
+        double *d_sums = nullptr;
+        unsigned long long *d_counts = nullptr;
+        int32_t *d_assign = nullptr;
+        cudaError_t e = cudaMalloc((void **)&d_sums, KD * 8);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&d_counts, (size_t)K * 8);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&d_assign, s.n * 4);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_sums, 0, KD * 8, s.stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d_counts, 0, (size_t)K * 8, s.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_assign, assign_host + off, s.n * 4, cudaMemcpyHostToDevice, s.stream);
+        int rc = e == cudaSuccess ? nk::cluster_sums(static_cast<const float *>(s.rows), s.n, ix->dim, d_assign, K, d_sums, d_counts, s.stream) : -1;
+        if (rc == 0) {
+            e = cudaMemcpyAsync(part.data(), d_sums, KD * 8, cudaMemcpyDeviceToHost, s.stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(cpart.data(), d_counts, (size_t)K * 8, cudaMemcpyDeviceToHost, s.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+        }
+        if (e != cudaSuccess) { nk::set_error("nk_index_cluster_means: %s", cudaGetErrorString(e)); cudaGetLastError(); rc = -1; }
+        cudaStreamSynchronize(s.stream);
+        cudaFree(d_sums); cudaFree(d_counts); cudaFree(d_assign);
+        if (rc != 0) return -1;
+        ix->stats.kernel_launches++;
+        for (size_t i = 0; i < KD; ++i) sums[i] += part[i];
+        for (uint32_t c = 0; c < K; ++c) counts[c] += cpart[c];
+        off += s.n;
+    }
+    for (uint32_t c = 0; c < K; ++c) {
+        if (counts[c])
+            for (uint32_t d = 0; d < ix->dim; ++d) centroids_io[(size_t)c * ix->dim + d] = (float)(sums[(size_t)c * ix->dim + d] / (double)counts[c]);
+        if (counts_out) counts_out[c] = (uint32_t)counts[c];
+    }
+    return 0;
 }
 
 int nk_fill_uniform_device(int device_id, float *out_dev, uint64_t n_rows, uint32_t dim, uint64_t seed,

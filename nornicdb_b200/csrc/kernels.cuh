@@ -26,7 +26,7 @@ struct Workspace {
     float *qaux = nullptr;        size_t qaux_bytes = 0;     // tensor path: split / normalised queries
     float *rownorm = nullptr;     size_t rownorm_bytes = 0;  // tensor path: per-row inverse norms / sq norms
     int *flags = nullptr;   // 8 ints: [0] candidate-buffer overflow (must stay 0), [1] filter-margin overflow, [2] max |x|^2
-                            // bits, [3] longest list, [4]/[6] BF16 bound maxima, [5] retry-stage marker (scan_tensor_shared.cuh)
+                            // bits, [4]/[6] BF16 bound maxima, [5] retry-stage marker, [7] longest list (scan_tensor_shared.cuh)
     int release();
 };
 int ws_reserve(void **p, size_t *cur, size_t need);
@@ -80,6 +80,11 @@ int topk_scores(const DeviceInfo &di, const float *scores, uint32_t n, uint32_t 
 // below[q] = keys[q*k + k-1] (the smallest key pass p returned): the exclusion bound of pass p+1.
 int update_below(const uint64_t *keys, uint32_t Q, uint32_t k, uint64_t *below, cudaStream_t s);
 int fill_uniform(void *out, int dtype, uint64_t n_rows, uint32_t dim, uint64_t seed, uint64_t row_base, cudaStream_t s);
+// k-means update step on device (kmeans.go:585-618): fp64 per-cluster sums + member counts (the K x dim means are
+// finished on the host); count_changed = |{i : a[i] != b[i]}| accumulated into *changed.
+int cluster_sums(const float *rows, uint64_t n, uint32_t dim, const int32_t *assign, uint32_t K, double *sums,
+                 unsigned long long *counts, cudaStream_t s);
+int count_changed(const int32_t *a, const uint32_t *b, uint64_t n, unsigned long long *changed, cudaStream_t s);
 int gather_rows(const void *rows, int dtype, uint32_t dim, const uint32_t *idx, uint32_t n_idx, void *out,
                 cudaStream_t s);
 

@@ -99,6 +99,32 @@ __global__ void gather_rows_kernel(const T *rows, uint32_t dim, const uint32_t *
     }
 }
 
+// ---- k-means update step (pkg/gpu/kmeans.go:585-618) -------------------------------------------------------------
+// Per-cluster float64 sums of the member rows: one warp per row, lanes stride the dimensions, fp64 atomic adds (the
+// K x dim accumulator is spread over L2, so contention is low; fp64 keeps the sum order-independent to ~1e-16, far
+// below the float32 the mean is rounded to).  Rows whose assignment is outside [0, K) are skipped.
+__global__ void cluster_sums_kernel(const float *rows, uint64_t n, uint32_t dim, const int32_t *assign, uint32_t K, double *sums,
+                                    unsigned long long *counts) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t row = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps) {
+        const int32_t c = assign[row];
+        if (c < 0 || (uint32_t)c >= K) continue;
+        const float *x = rows + row * dim;
+        double *dst = sums + (size_t)c * dim;
+        for (uint32_t j = lane; j < dim; j += 32) atomicAdd(dst + j, (double)x[j]);
+        if (lane == 0) atomicAdd(counts + c, 1ull);
+    }
+}
+// changed += (a[i] != b[i])
+__global__ void count_changed_kernel(const int32_t *a, const uint32_t *b, uint64_t n, unsigned long long *changed) {
+    unsigned long long mine = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        mine += a[i] != (int32_t)b[i];
+    mine = __reduce_add_sync(0xffffffffu, (unsigned)mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(changed, mine);
+}
+
 static inline unsigned warp_grid(uint32_t n) {
     uint64_t blocks = ((uint64_t)n + 7) / 8;  // 8 warps per 256-thread block
     if (blocks > 148 * 16) blocks = 148 * 16;
@@ -133,6 +159,19 @@ int fill_uniform(void *out, int dtype, uint64_t n_rows, uint32_t dim, uint64_t s
         fill_uniform_kernel<__half><<<grid, 256, 0, s>>>((__half *)out, total, dim, seed, row_base);
     else
         fill_uniform_kernel<float><<<grid, 256, 0, s>>>((float *)out, total, dim, seed, row_base);
+    NK_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int cluster_sums(const float *rows, uint64_t n, uint32_t dim, const int32_t *assign, uint32_t K, double *sums,
+                 unsigned long long *counts, cudaStream_t s) {
+    if (n == 0) return 0;
+    cluster_sums_kernel<<<148 * 8, 256, 0, s>>>(rows, n, dim, assign, K, sums, counts);
+    NK_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int count_changed(const int32_t *a, const uint32_t *b, uint64_t n, unsigned long long *changed, cudaStream_t s) {
+    if (n == 0) return 0;
+    count_changed_kernel<<<148 * 4, 256, 0, s>>>(a, b, n, changed);
     NK_CUDA_OK(cudaGetLastError());
     return 0;
 }

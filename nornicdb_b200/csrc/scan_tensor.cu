@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t j = tid; j < p.dim; j += FINISH_THREADS) qs[j] = p.queries[(size_t)q * p.dim + j];
     int n = p.gcount[q];
-    if (tid == 0) atomicMax(p.flags + 3, n);  // diagnostics: longest shared list of this search
+    if (tid == 0) atomicMax(p.flags + 7, n);  // diagnostics: longest shared list of this search
     if (n > (int)p.list_cap) n = (int)p.list_cap;
     __syncthreads();
     if (warp == 0) {

@@ -36,7 +36,7 @@ struct Params {
     uint32_t *gtau;           // filter: [Q] cross-CTA shared threshold (order-preserving bits, atomicMax; 0 = none yet)
     int *gcount;              // filter: [Q] fill of the shared append lists
     int *flags;               // [0] fatal buffer overflow, [1] filter-margin overflow (-> next stage), [2] max |x|^2 bits,
-                              // [3] longest list (diagnostics), [4] / [6] BF16 max ra / rb bits, [5] retry-stage marker
+                              // [4] / [6] BF16 max ra / rb bits, [5] retry-stage marker, [7] longest list (diagnostics)
     const int *only_if;       // exact fallback: run only if *only_if != 0
     int debug;                // NK_TC_DEBUG bit 64: clock64 wait-time instrumentation of CTA 0
 };

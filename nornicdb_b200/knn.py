@@ -161,6 +161,31 @@ class KnnIndex:
                                              sc.ctypes.data_as(C.c_void_p)), "nk_score_subset")
         return idx[:ke], sc[:ke]
 
+    # ---- k-means routing on device (pkg/gpu/kmeans.go) ----------------------------------------------------------
+    def assign_nearest(self, centroids, assign: np.ndarray, metric: str = "euclidean") -> int:
+        """assignToCentroids (euclidean) / assignToCentroidsGPU (cosine): `assign` (int32 [rows]) is updated in place,
+        returns the number of changed assignments."""
+        c = np.ascontiguousarray(np.asarray(centroids, dtype=np.float32))
+        if c.ndim != 2 or c.shape[1] != self.dim:
+            raise KnnError(f"invalid dimensions: centroids {c.shape}, index has {self.dim}")
+        if assign.dtype != np.int32 or not assign.flags.c_contiguous or assign.size != len(self):
+            raise KnnError("assign must be a contiguous int32 array with one entry per row")
+        changed = C.c_uint64(0)
+        _check(self.lib.nk_index_assign_nearest(self.ptr, c.ctypes.data_as(C.c_void_p), c.shape[0], METRICS[metric],
+                                                assign.ctypes.data_as(C.c_void_p), C.byref(changed)), "nk_index_assign_nearest")
+        return int(changed.value)
+
+    def cluster_means(self, assign: np.ndarray, centroids) -> Tuple[np.ndarray, np.ndarray]:
+        """updateCentroidsWithBuffer: returns (new centroids float32 [K x dim], member counts uint32 [K])."""
+        c = np.array(centroids, dtype=np.float32, order="C", copy=True)
+        a = np.ascontiguousarray(assign, dtype=np.int32)
+        if a.size != len(self):
+            raise KnnError("assign must have one entry per row")
+        counts = np.zeros(c.shape[0], dtype=np.uint32)
+        _check(self.lib.nk_index_cluster_means(self.ptr, a.ctypes.data_as(C.c_void_p), c.shape[0], c.ctypes.data_as(C.c_void_p),
+                                               counts.ctypes.data_as(C.c_void_p)), "nk_index_cluster_means")
+        return c, counts
+
 
 def merge_keys_device(device_id: int, keys_ptr: int, n_lists: int, Q: int, k: int, metric: str, out_idx_ptr: int,
                       out_score_ptr: int, stream: int = 0) -> None:

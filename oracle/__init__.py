@@ -64,6 +64,12 @@ def lib() -> C.CDLL:
         L.orc_scores_exact64.restype = None
         L.orc_scores_exact64.argtypes = [vp, i, u64, u32, vp, i, vp]
         L.orc_num_threads.restype = i
+        L.orc_sq_euclid64.restype = C.c_double
+        L.orc_sq_euclid64.argtypes = [vp, vp, sz]
+        L.orc_kmeans_assign.restype = u64
+        L.orc_kmeans_assign.argtypes = [vp, u64, u32, vp, u32, i, vp]
+        L.orc_kmeans_update.restype = None
+        L.orc_kmeans_update.argtypes = [vp, u64, u32, vp, u32, vp, vp]
         for name in ("sb_dot", "sb_cosine", "sb_euclid"):
             getattr(L, name).restype = C.c_float
             getattr(L, name).argtypes = [vp, vp, sz]
@@ -184,6 +190,32 @@ def scores_exact64(rows, query, metric):
     m = METRICS[metric] if isinstance(metric, str) else metric
     lib().orc_scores_exact64(_p(rows), dt, rows.shape[0], rows.shape[1], _p(q), m, _p(out))
     return out
+
+
+def sq_euclid64(a, b) -> float:
+    """squaredEuclidean, kmeans.go:430-454."""
+    a, b = _f32(a), _f32(b)
+    assert a.size == b.size
+    return float(lib().orc_sq_euclid64(_p(a), _p(b), a.size))
+
+
+def kmeans_assign(rows, centroids, assign, by_cosine=False):
+    """assignToCentroids / assignToCentroidsGPU (kmeans.go:458-546).  `assign` (int32 [n]) is updated in place; returns
+    the number of changed assignments."""
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    cen = np.ascontiguousarray(centroids, dtype=np.float32)
+    assert assign.dtype == np.int32 and assign.flags.c_contiguous and assign.size == rows.shape[0]
+    return int(lib().orc_kmeans_assign(_p(rows), rows.shape[0], rows.shape[1], _p(cen), cen.shape[0], int(bool(by_cosine)), _p(assign)))
+
+
+def kmeans_update(rows, assign, centroids):
+    """updateCentroidsWithBuffer (kmeans.go:585-618): returns (new centroids, counts); empty clusters keep their position."""
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    cen = np.array(centroids, dtype=np.float32, order="C", copy=True)
+    a = np.ascontiguousarray(assign, dtype=np.int32)
+    counts = np.zeros(cen.shape[0], dtype=np.uint32)
+    lib().orc_kmeans_update(_p(rows), rows.shape[0], rows.shape[1], _p(a), cen.shape[0], _p(cen), _p(counts))
+    return cen, counts
 
 
 def simd_knn(rows, queries, k, metric, threads=1):

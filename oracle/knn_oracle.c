@@ -24,6 +24,7 @@
  * Compile WITHOUT fast-math (oracle/Makefile: -O2 -ffp-contract=off) so fp32 sums are the
  * sequential sums the Go code produces.
  */
+#include <float.h>
 #include <math.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -400,4 +401,72 @@ int orc_num_threads(void) {
 #else
     return 1;
 #endif
+}
+
+/* ======================================================================================================
+ * k-means routing (pkg/gpu/kmeans.go) — SURVEY.md §8(f)4
+ * ====================================================================================================== */
+
+/* squaredEuclidean — kmeans.go:430-454: float32 differences, float64 squares in four interleaved sums. */
+double orc_sq_euclid64(const float *a, const float *b, size_t n) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    size_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        double d0 = (double)(a[i] - b[i]), d1 = (double)(a[i + 1] - b[i + 1]);
+        double d2 = (double)(a[i + 2] - b[i + 2]), d3 = (double)(a[i + 3] - b[i + 3]);
+        s0 += d0 * d0; s1 += d1 * d1; s2 += d2 * d2; s3 += d3 * d3;
+    }
+    for (; i < n; i++) {
+        double d = (double)(a[i] - b[i]);
+        s0 += d * d;
+    }
+    return s0 + s1 + s2 + s3;
+}
+
+/* assignToCentroids — kmeans.go:458-489 (by_cosine = 0: nearest by squaredEuclidean, strict <) and
+ * assignToCentroidsGPU — kmeans.go:491-546 (by_cosine = 1: highest cosineSimilarityFlat, strict >).
+ * assign[] is updated in place; returns the number of assignments that changed. */
+uint64_t orc_kmeans_assign(const float *rows, uint64_t n, uint32_t dim, const float *centroids, uint32_t k, int by_cosine,
+                           int32_t *assign) {
+    uint64_t changed = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const float *x = rows + i * dim;
+        int32_t nearest = 0;
+        if (by_cosine) {
+            float best = -FLT_MAX;
+            for (uint32_t c = 0; c < k; c++) {
+                float sim = orc_cosine_flat(centroids + (size_t)c * dim, dim, x, dim);
+                if (sim > best) { best = sim; nearest = (int32_t)c; }
+            }
+        } else {
+            double best = DBL_MAX;
+            for (uint32_t c = 0; c < k; c++) {
+                double d = orc_sq_euclid64(x, centroids + (size_t)c * dim, dim);
+                if (d < best) { best = d; nearest = (int32_t)c; }
+            }
+        }
+        if (assign[i] != nearest) { assign[i] = nearest; changed++; }
+    }
+    return changed;
+}
+
+/* updateCentroidsWithBuffer — kmeans.go:585-618: float64 sums, mean rounded to float32, empty clusters keep
+ * their previous position.  counts (k) may be NULL. */
+void orc_kmeans_update(const float *rows, uint64_t n, uint32_t dim, const int32_t *assign, uint32_t k, float *centroids,
+                       uint32_t *counts) {
+    double *sums = (double *)calloc((size_t)k * dim, sizeof(double));
+    uint64_t *cnt = (uint64_t *)calloc(k, sizeof(uint64_t));
+    for (uint64_t i = 0; i < n; i++) {
+        int32_t c = assign[i];
+        if (c < 0 || (uint32_t)c >= k) continue;
+        cnt[c]++;
+        for (uint32_t d = 0; d < dim; d++) sums[(size_t)c * dim + d] += (double)rows[i * dim + d];
+    }
+    for (uint32_t c = 0; c < k; c++) {
+        if (cnt[c] > 0)
+            for (uint32_t d = 0; d < dim; d++) centroids[(size_t)c * dim + d] = (float)(sums[(size_t)c * dim + d] / (double)cnt[c]);
+        if (counts) counts[c] = (uint32_t)cnt[c];
+    }
+    free(sums);
+    free(cnt);
 }

@@ -114,6 +114,22 @@ add("search.vector_index", "pkg/search/search_test.go:25-52",
 # ---- pkg/gpu/kmeans_test.go:698-717 (next-row KAT: squared euclidean)
 add("kmeans.squared_euclidean", "pkg/gpu/kmeans_test.go:698-717", a=[1, 2, 3], b=[4, 5, 6], want=27.0, tol=1e-4)
 add("kmeans.squared_euclidean", "pkg/gpu/kmeans_test.go:698-717", a=[3, 4, 0], b=[0, 0, 0], want=25.0, tol=1e-4)
+add("kmeans.squared_euclidean", "pkg/gpu/kmeans_test.go:698-717", a=[0, 0, 0], b=[0, 0, 0], want=0.0, tol=1e-4)
+add("kmeans.squared_euclidean", "pkg/gpu/kmeans_test.go:698-717", a=[1, 0, 0], b=[0, 0, 0], want=1.0, tol=1e-4)
+add("kmeans.squared_euclidean", "pkg/gpu/kmeans_test.go:698-717", a=[1, 1, 1], b=[0, 0, 0], want=3.0, tol=1e-4)
+
+# ---- pkg/gpu/kmeans_test.go:675-696 TestOptimalK (k = clamp(sqrt(n/2), 10, 1000), kmeans.go:323-332)
+for n, lo, hi in [(100, 10, 10), (200, 10, 10), (800, 10, 30), (2000, 20, 50), (10000, 50, 100), (2000000, 1000, 1000)]:
+    add("kmeans.optimal_k", "pkg/gpu/kmeans_test.go:675-696", n=n, want_min=lo, want_max=hi)
+
+# ---- pkg/gpu/kmeans_test.go:744-800 TestClusterIndex_SearchCandidates: 20 embeddings, emb_i[i % dims] = i (testDims = 64,
+# kmeans_test.go:60), query e0; result length = min(topK, |candidates|), empty candidates -> 0, wrong dims -> error
+S = "pkg/gpu/kmeans_test.go:744-800"
+E0, Z = [1.0] + [0.0] * 63, [0.0] * 64
+add("kmeans.search_candidates", S, dims=64, n=20, query=E0, candidates=[0, 1, 2, 3, 4], topk=3, want_len=3)
+add("kmeans.search_candidates", S, dims=64, n=20, query=Z, candidates=[], topk=3, want_len=0)
+add("kmeans.search_candidates", S, dims=64, n=20, query=Z, candidates=[0, 1, 2], topk=100, want_len=3)
+add("kmeans.search_candidates", S, dims=64, n=20, query=Z + [0.0], candidates=[0, 1], topk=1, want_error="ErrInvalidDimensions")
 
 # ---- pkg/cypher/vector_procedures_test.go:538-572
 add("cypher.query_nodes_score", "pkg/cypher/vector_procedures_test.go:538-572", stored=[0.7, 0.2, 0.05, 0.05],

@@ -62,7 +62,8 @@ def test_10m_rows_properties(knn_lib, oracle_mod, metric, k):
         planted[j] = row
     ix.set_path("shadow")
     hi, hs = ix.search(q, k)
-    assert ix.debug_flags()[:2] == [0, 0]   # no retry stage was needed
+    fl = ix.debug_flags()
+    assert fl[:2] == [0, 0] and fl[3] == 0, fl   # no retry stage was needed
     ix.set_path("filter")
     fi, fs = ix.search(q, k)
     assert ix.debug_flags()[:2] == [0, 0]

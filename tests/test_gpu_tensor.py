@@ -119,16 +119,18 @@ def test_shadow_parity(knn_lib, oracle_mod, metric, shape):
     assert run_tc(oracle_mod, n, d, Q, k, metric, path="shadow") <= Q * k // 2000
 
 
-def test_filter_equals_simt_bitwise_on_indices(knn_lib, oracle_mod):
-    """Final scores come from exact fp32 rescoring, so the filter path and the CUDA-core scan agree on every index."""
+@pytest.mark.parametrize("path", ["filter", "shadow"])
+def test_filter_equals_simt_bitwise_on_indices(knn_lib, oracle_mod, path):
+    """Final scores come from exact fp32 rescoring, so the filter paths and the CUDA-core scan agree on every index."""
     from nornicdb_b200.knn import KnnIndex
     rows = oracle_mod.fill_uniform(30_000, 512, 3)
     q = oracle_mod.fill_uniform(64, 512, 4)
     ix = KnnIndex(512, metric="cosine")
     ix.upload(rows)
-    ix.set_path("filter")
+    ix.set_path(path)
     fi, fs = ix.search(q, 10)
-    assert ix.debug_flags()[:2] == [0, 0]  # ordinary data: no overflow, no fallback
+    flags = ix.debug_flags()
+    assert flags[:2] == [0, 0] and flags[3] == 0, flags  # ordinary data: no overflow, no retry, no fallback
     ix.set_path("simt")
     si, ss = ix.search(q, 10)
     ix.release()
@@ -173,19 +175,20 @@ def test_shadow_margin_overflow_retries_with_tf32_then_exact(knn_lib, oracle_mod
     gi, gs = ix.search(q, 10)
     flags = ix.debug_flags()
     ix.release()
-    assert flags[0] == 0, flags
+    assert flags[0] == 0 and flags[3] == 1, flags  # the shadow stage did overflow; the TF32 stage re-ran the search
     oi, os_ = oracle_mod.knn_exact64(rows, q, 10, metric)
     check_parity(rows, q, 10, metric, gi, gs, oi, os_, swap_eps=5e-6)
 
 
-def test_filter_ties_and_zero_vectors(knn_lib, oracle_mod):
+@pytest.mark.parametrize("path", ["filter", "shadow"])
+def test_filter_ties_and_zero_vectors(knn_lib, oracle_mod, path):
     from nornicdb_b200.knn import KnnIndex
     base = oracle_mod.fill_uniform(16, 64, 5)
     rows = np.tile(base, (64, 1))
     rows[5] = 0.0
     for metric in ("cosine", "dot", "euclidean"):
         ix = KnnIndex(64, metric=metric)
-        ix.set_path("filter")
+        ix.set_path(path)
         ix.upload(rows)
         gi, gs = ix.search(base[3:4], 20)
         ix.release()

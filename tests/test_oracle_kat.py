@@ -81,6 +81,7 @@ def test_edge_cases(kats, oracle_mod):
             assert not math.isnan(o.cosine(t["a"], t["b"]))
         if t["op"] == "kmeans.squared_euclidean":
             assert abs(o.euclid(t["a"], t["b"]) ** 2 - t["want"]) <= 1e-3
+            assert abs(o.sq_euclid64(t["a"], t["b"]) - t["want"]) <= t["tol"]
         if t["op"] == "cypher.query_nodes_score":
             assert o.vec_cosine64(t["stored"], t["query"]) > t["want_gt"]
 
@@ -153,3 +154,31 @@ def test_generator_is_counter_based(oracle_mod):
     assert a.min() >= -1.0 and a.max() < 1.0
     h = o.fill_uniform(10, 16, 7, dtype="f16")
     assert (h == a.astype(np.float16)).all()
+
+
+def test_kmeans_restatement(kats, oracle_mod):
+    """pkg/gpu/kmeans.go: optimalK KATs (host mirror), assignment / update steps against plain float64 numpy."""
+    from nornicdb_b200.cluster_index import optimalK
+    seen = 0
+    for t in kats:
+        if t["op"] == "kmeans.optimal_k":
+            assert t["want_min"] <= optimalK(t["n"]) <= t["want_max"], t
+            seen += 1
+    assert seen == 6
+    rng = np.random.default_rng(0)
+    rows = rng.uniform(-1, 1, (500, 24)).astype(np.float32)
+    cen = rng.uniform(-1, 1, (7, 24)).astype(np.float32)
+    a = np.zeros(500, dtype=np.int32)
+    changed = oracle_mod.kmeans_assign(rows, cen, a)
+    d = ((rows[:, None, :].astype(np.float64) - cen[None].astype(np.float64)) ** 2).sum(-1)
+    assert (a == d.argmin(1)).all() and changed == int((d.argmin(1) != 0).sum())
+    assert oracle_mod.kmeans_assign(rows, cen, a) == 0
+    ac = np.zeros(500, dtype=np.int32)
+    oracle_mod.kmeans_assign(rows, cen, ac, by_cosine=True)
+    cos = (rows @ cen.T) / np.sqrt((rows * rows).sum(1)[:, None] * (cen * cen).sum(1)[None])
+    assert (ac == cos.argmax(1)).mean() > 0.995
+    new, counts = oracle_mod.kmeans_update(rows, a, cen)
+    for c in range(7):
+        assert counts[c] == (a == c).sum()
+        if counts[c]:
+            assert np.allclose(new[c], rows[a == c].astype(np.float64).mean(0), rtol=1e-6, atol=1e-7)
