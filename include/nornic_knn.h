@@ -125,6 +125,15 @@ void nk_index_release(NkIndex *ix); /* NULL-safe */
  * Replaces syncToCUDA's NewBuffer + NormalizeVectors (gpu.go:2073-2118): rows are stored RAW; cosine
  * normalisation happens inside the search kernel, so device rows always equal host rows. */
 int nk_index_upload(NkIndex *ix, const void *rows_host, uint64_t n_rows);
+/* The same from fp32 host rows whatever the dtype of the index: an fp16 index converts on the device while loading
+ * (round to nearest even).  Uploads stream through two pinned staging buffers, so pageable or unaligned sources load
+ * at the PCIe / host-memcpy rate. */
+int nk_index_upload_from_f32(NkIndex *ix, const float *rows_host_f32, uint64_t n_rows);
+/* Locate the vectors inside a serialized index (EmbeddingIndex.Serialize, gpu.go:2373-2412: LE [dims u32][count u32]
+ * [count x (len u32, id bytes)][count x dims fp32]) so that they can be fed straight to nk_index_upload_from_f32 —
+ * the ids are the host language's business.  vec_offset has no alignment guarantee.  0 / -1 ("gpu: invalid
+ * serialized data" for blobs shorter than the header, gpu.go:2419-2421). */
+int nk_blob_vectors(const void *blob, size_t blob_bytes, uint32_t *dims, uint32_t *count, size_t *vec_offset);
 /* Append rows to the last shard without re-uploading the rest (EmbeddingIndex.Add, gpu.go:1378-1434). */
 int nk_index_append(NkIndex *ix, const void *rows_host, uint64_t n_rows);
 /* Overwrite row `row` (global index) in place (EmbeddingIndex.Add on an existing id, gpu.go:1391-1399). */

@@ -10,6 +10,7 @@
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -38,6 +39,11 @@ struct NkShard {
     nk::Workspace ws;
     uint64_t *h_keys = nullptr;  // pinned staging for multi-shard host merge
     size_t h_keys_bytes = 0;
+    // cold-start feed: two pinned staging buffers + their "copy drained" events (stream_h2d)
+    void *stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    void *cvt = nullptr;  // device scratch for fp32 -> fp16 conversion at load
+    size_t cvt_bytes = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // pending scan-kernel event pairs
     std::vector<uint64_t> timing_launches;
 };
@@ -107,6 +113,56 @@ static int shard_shadow_row(NkIndex *ix, NkShard &s, uint64_t local) {  // one r
     if (!s.shadow || local >= s.shadow_n) return 0;
     ix->stats.kernel_launches++;
     return nk::build_shadow(static_cast<const float *>(s.rows), local, 1, ix->dim, ix->dimpad(), s.shadow, s.xnorm2, s.dnorm2, s.stream);
+}
+
+// ---- cold-start feed ---------------------------------------------------------------------------
+// Host rows -> device through two pinned staging buffers: while chunk i crosses PCIe by DMA the CPU copies chunk i+1
+// into the other buffer, so pageable (and unaligned: the vectors of a serialized index start at an arbitrary byte
+// offset) sources load at the slower of the host memcpy and the PCIe rate instead of the driver's pageable path.
+// cvt_f32_to_f16: the source is fp32 and the destination rows are fp16 (down-conversion at load, on the device).
+constexpr size_t STAGE_BYTES = 32u << 20;
+
+// one core copies ~11 GB/s, a x16 Gen5 link moves ~50: split the staging copy over a few threads
+static void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+    constexpr int T = 6;
+    if (bytes < (4u << 20)) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::thread th[T - 1];
+    const size_t part = (bytes / T + 63) & ~(size_t)63;
+    for (int t = 1; t < T; ++t) {
+        const size_t lo = std::min(bytes, part * t), hi = t == T - 1 ? bytes : std::min(bytes, part * (t + 1));
+        th[t - 1] = std::thread([=] { if (hi > lo) memcpy(static_cast<char *>(dst) + lo, static_cast<const char *>(src) + lo, hi - lo); });
+    }
+    memcpy(dst, src, std::min(bytes, part));
+    for (auto &t : th) t.join();
+}
+
+static int stream_h2d(NkShard &s, void *dst_dev, const void *src_host, size_t bytes, bool cvt_f32_to_f16 = false) {
+    if (bytes == 0) return 0;
+    for (int i = 0; i < 2; ++i) {
+        if (!s.stage[i]) NK_CUDA_OK(cudaHostAlloc(&s.stage[i], STAGE_BYTES, cudaHostAllocDefault));
+        if (!s.stage_ev[i]) NK_CUDA_OK(cudaEventCreateWithFlags(&s.stage_ev[i], cudaEventDisableTiming));
+    }
+    if (cvt_f32_to_f16 && nk::ws_reserve(&s.cvt, &s.cvt_bytes, 2 * STAGE_BYTES)) return -1;
+    size_t done = 0;
+    for (int i = 0; done < bytes; ++i) {
+        const int b = i & 1;
+        const size_t chunk = std::min(STAGE_BYTES, bytes - done);
+        if (i >= 2) NK_CUDA_OK(cudaEventSynchronize(s.stage_ev[b]));  // the DMA that last read this buffer has drained
+        parallel_memcpy(s.stage[b], static_cast<const char *>(src_host) + done, chunk);
+        if (cvt_f32_to_f16) {
+            float *scratch = reinterpret_cast<float *>(static_cast<char *>(s.cvt) + (size_t)b * STAGE_BYTES);
+            NK_CUDA_OK(cudaMemcpyAsync(scratch, s.stage[b], chunk, cudaMemcpyHostToDevice, s.stream));
+            if (nk::convert_f32_to_f16(scratch, static_cast<char *>(dst_dev) + done / 2, chunk / 4, s.stream)) return -1;
+        } else {
+            NK_CUDA_OK(cudaMemcpyAsync(static_cast<char *>(dst_dev) + done, s.stage[b], chunk, cudaMemcpyHostToDevice, s.stream));
+        }
+        NK_CUDA_OK(cudaEventRecord(s.stage_ev[b], s.stream));
+        done += chunk;
+    }
+    return 0;
 }
 
 static int shard_reserve_rows(NkIndex *ix, NkShard &s, uint64_t need_rows, bool keep) {
@@ -287,16 +343,22 @@ void nk_index_release(NkIndex *ix) {
         if (s.rows && s.owns) cudaFree(s.rows);
         shard_drop_shadow(s);
         if (s.h_keys) cudaFreeHost(s.h_keys);
+        for (int i = 0; i < 2; ++i) {
+            if (s.stage[i]) cudaFreeHost(s.stage[i]);
+            if (s.stage_ev[i]) cudaEventDestroy(s.stage_ev[i]);
+        }
+        if (s.cvt) cudaFree(s.cvt);
         s.ws.release();
     }
     delete ix;
 }
 
-int nk_index_upload(NkIndex *ix, const void *rows_host, uint64_t n_rows) {
+static int upload_impl(NkIndex *ix, const void *rows_host, uint64_t n_rows, bool src_is_f32) {
     if (!ix) { nk::set_error("null index"); return -1; }
     if (n_rows && !rows_host) { nk::set_error("null rows"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
-    const size_t rb = (size_t)ix->dim * ix->esz();
+    const bool cvt = src_is_f32 && ix->dtype == NK_DTYPE_F16;
+    const size_t rb = (size_t)ix->dim * ix->esz(), src_rb = (size_t)ix->dim * (cvt ? 4 : ix->esz());
     const uint64_t G = ix->shards.size();
     if (n_rows / G + 1 > 0xfffffff0ull) { nk::set_error("shard exceeds 2^32 rows"); return -1; }
     uint64_t off = 0;
@@ -307,18 +369,44 @@ int nk_index_upload(NkIndex *ix, const void *rows_host, uint64_t n_rows) {
         if (!s.owns) { s.rows = nullptr; s.owns = true; s.cap = 0; }
         s.n = 0;
         if (shard_reserve_rows(ix, s, cnt, false)) return -1;
-        if (cnt) NK_CUDA_OK(cudaMemcpyAsync(s.rows, (const char *)rows_host + off * rb, cnt * rb, cudaMemcpyHostToDevice, s.stream));
+        if (stream_h2d(s, s.rows, static_cast<const char *>(rows_host) + off * src_rb, cnt * src_rb, cvt)) return -1;
         s.n = cnt;
         s.shadow_n = 0;
         if (shard_sync_shadow(ix, s)) return -1;
         off += cnt;
-        ix->stats.bytes_h2d += cnt * rb;
+        ix->stats.bytes_h2d += cnt * src_rb;
     }
     for (auto &s : ix->shards) {
         NK_CUDA_OK(cudaSetDevice(s.device));
         NK_CUDA_OK(cudaStreamSynchronize(s.stream));
     }
     rebase(ix);
+    (void)rb;
+    return 0;
+}
+
+int nk_index_upload(NkIndex *ix, const void *rows_host, uint64_t n_rows) { return upload_impl(ix, rows_host, n_rows, false); }
+
+int nk_index_upload_from_f32(NkIndex *ix, const float *rows_host_f32, uint64_t n_rows) { return upload_impl(ix, rows_host_f32, n_rows, true); }
+
+// Serialized index (EmbeddingIndex.Serialize, gpu.go:2373-2412): LE [dims u32][count u32][count x (len u32, id bytes)]
+// [count x dims fp32].  Walks the id table; the vectors start at *vec_offset (any byte alignment).
+int nk_blob_vectors(const void *blob, size_t blob_bytes, uint32_t *dims, uint32_t *count, size_t *vec_offset) {
+    if (!blob || !dims || !count || !vec_offset) { nk::set_error("null argument"); return -1; }
+    const unsigned char *p = static_cast<const unsigned char *>(blob);
+    auto rd32 = [&](size_t at) { return (uint32_t)p[at] | ((uint32_t)p[at + 1] << 8) | ((uint32_t)p[at + 2] << 16) | ((uint32_t)p[at + 3] << 24); };
+    if (blob_bytes < 8) { nk::set_error("gpu: invalid serialized data"); return -1; }  // gpu.go:2419-2421
+    const uint32_t d = rd32(0), c = rd32(4);
+    size_t off = 8;
+    for (uint32_t i = 0; i < c; ++i) {
+        if (off + 4 > blob_bytes) { nk::set_error("serialized index truncated in the id table (id %u)", i); return -1; }
+        const uint32_t len = rd32(off);
+        off += 4;
+        if (len > blob_bytes - off) { nk::set_error("serialized index truncated in the id table (id %u)", i); return -1; }
+        off += len;
+    }
+    if ((uint64_t)c * d * 4 > blob_bytes - off) { nk::set_error("serialized index truncated: %u x %u vectors do not fit", c, d); return -1; }
+    *dims = d; *count = c; *vec_offset = off;
     return 0;
 }
 
@@ -332,7 +420,7 @@ int nk_index_append(NkIndex *ix, const void *rows_host, uint64_t n_rows) {
     if (s.n + n_rows > 0xfffffff0ull) { nk::set_error("shard exceeds 2^32 rows"); return -1; }
     NK_CUDA_OK(cudaSetDevice(s.device));
     if (shard_reserve_rows(ix, s, s.n + n_rows, true)) return -1;
-    NK_CUDA_OK(cudaMemcpyAsync((char *)s.rows + s.n * rb, rows_host, n_rows * rb, cudaMemcpyHostToDevice, s.stream));
+    if (stream_h2d(s, (char *)s.rows + s.n * rb, rows_host, n_rows * rb)) return -1;
     s.n += n_rows;
     if (shard_sync_shadow(ix, s)) return -1;  // converts only the appended rows (all of them if the shard was regrown)
     NK_CUDA_OK(cudaStreamSynchronize(s.stream));

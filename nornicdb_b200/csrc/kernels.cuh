@@ -85,6 +85,7 @@ int fill_uniform(void *out, int dtype, uint64_t n_rows, uint32_t dim, uint64_t s
 int cluster_sums(const float *rows, uint64_t n, uint32_t dim, const int32_t *assign, uint32_t K, double *sums,
                  unsigned long long *counts, cudaStream_t s);
 int count_changed(const int32_t *a, const uint32_t *b, uint64_t n, unsigned long long *changed, cudaStream_t s);
+int convert_f32_to_f16(const float *src, void *dst_half, size_t n, cudaStream_t s);  // round to nearest even, like the host's astype
 int gather_rows(const void *rows, int dtype, uint32_t dim, const uint32_t *idx, uint32_t n_idx, void *out,
                 cudaStream_t s);
 

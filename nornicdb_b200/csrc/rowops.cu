@@ -116,6 +116,9 @@ __global__ void cluster_sums_kernel(const float *rows, uint64_t n, uint32_t dim,
         if (lane == 0) atomicAdd(counts + c, 1ull);
     }
 }
+__global__ void convert_f32_to_f16_kernel(const float *src, __half *dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = __float2half_rn(src[i]);
+}
 // changed += (a[i] != b[i])
 __global__ void count_changed_kernel(const int32_t *a, const uint32_t *b, uint64_t n, unsigned long long *changed) {
     unsigned long long mine = 0;
@@ -166,6 +169,12 @@ int cluster_sums(const float *rows, uint64_t n, uint32_t dim, const int32_t *ass
                  unsigned long long *counts, cudaStream_t s) {
     if (n == 0) return 0;
     cluster_sums_kernel<<<148 * 8, 256, 0, s>>>(rows, n, dim, assign, K, sums, counts);
+    NK_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int convert_f32_to_f16(const float *src, void *dst, size_t n, cudaStream_t s) {
+    if (n == 0) return 0;
+    convert_f32_to_f16_kernel<<<148 * 8, 256, 0, s>>>(src, static_cast<__half *>(dst), n);
     NK_CUDA_OK(cudaGetLastError());
     return 0;
 }

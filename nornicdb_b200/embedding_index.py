@@ -11,6 +11,7 @@ pkg/gpu/gpu_test.go.  Differences, all on purpose:
 Only node-id strings live on the host ("NEVER transferred to GPU", gpu.go:1228-1231)."""
 from __future__ import annotations
 
+import ctypes as C
 import struct
 import threading
 from dataclasses import dataclass
@@ -18,7 +19,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .knn import KnnError, KnnIndex
+from .knn import KnnError, KnnIndex, blob_vectors
 
 
 class ErrInvalidDimensions(ValueError):  # gpu.go ErrInvalidDimensions
@@ -224,8 +225,12 @@ class EmbeddingIndex:
             off += 4
             ids.append(data[off:off + ln].decode("utf-8"))
             off += ln
-        vec = np.frombuffer(data, dtype="<f4", count=count * dims, offset=off).reshape(count, dims)
+        _, _, voff = blob_vectors(data)  # validates the table and the payload length
+        assert voff == off
         with self.mu:
-            self._ix.upload(vec.astype(self._np_dtype))  # the blob streams straight to device memory
+            # the fp32 payload (arbitrarily aligned inside the blob) streams straight to device memory through the
+            # library's pinned double buffer; an fp16 index converts on the device while loading
+            base = C.cast(C.c_char_p(data), C.c_void_p).value
+            self._ix.upload_from_f32(ptr=base + voff, n_rows=count)
             self.nodeIDs = ids
             self.idToIndex = {nid: i for i, nid in enumerate(ids)}

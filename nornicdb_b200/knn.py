@@ -69,6 +69,14 @@ class KnnIndex:
         a = self._rows(rows)
         _check(self.lib.nk_index_upload(self.ptr, a.ctypes.data_as(C.c_void_p), a.shape[0]), "nk_index_upload")
 
+    def upload_from_f32(self, rows=None, ptr: Optional[int] = None, n_rows: Optional[int] = None) -> None:
+        """Upload fp32 host rows whatever the dtype of the index (fp16 indexes convert on the device while loading).
+        Either a [n x dim] array, or a raw host address + row count (e.g. the payload of a serialized index)."""
+        if ptr is None:
+            a = np.ascontiguousarray(np.asarray(rows, dtype=np.float32)).reshape(-1, self.dim)
+            ptr, n_rows = a.ctypes.data, a.shape[0]
+        _check(self.lib.nk_index_upload_from_f32(self.ptr, C.c_void_p(ptr), int(n_rows)), "nk_index_upload_from_f32")
+
     def append(self, rows) -> None:
         a = self._rows(rows)
         _check(self.lib.nk_index_append(self.ptr, a.ctypes.data_as(C.c_void_p), a.shape[0]), "nk_index_append")
@@ -185,6 +193,13 @@ class KnnIndex:
         _check(self.lib.nk_index_cluster_means(self.ptr, a.ctypes.data_as(C.c_void_p), c.shape[0], c.ctypes.data_as(C.c_void_p),
                                                counts.ctypes.data_as(C.c_void_p)), "nk_index_cluster_means")
         return c, counts
+
+
+def blob_vectors(data: bytes) -> Tuple[int, int, int]:
+    """(dims, count, byte offset of the fp32 vectors) of a serialized index (gpu.go:2373-2412)."""
+    dims, count, off = C.c_uint32(0), C.c_uint32(0), C.c_size_t(0)
+    _check(_lib.load().nk_blob_vectors(C.c_char_p(data), len(data), C.byref(dims), C.byref(count), C.byref(off)), "nk_blob_vectors")
+    return int(dims.value), int(count.value), int(off.value)
 
 
 def merge_keys_device(device_id: int, keys_ptr: int, n_lists: int, Q: int, k: int, metric: str, out_idx_ptr: int,

@@ -77,3 +77,25 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "liboracle" not in text, f
+
+
+def test_blob_vectors_walks_the_id_table_without_a_gpu():
+    """nk_blob_vectors (host-only): locates the fp32 payload of EmbeddingIndex.Serialize's format (gpu.go:2373-2412)."""
+    import struct
+
+    import numpy as np
+    from nornicdb_b200.knn import KnnError, blob_vectors
+    ids = ["a", "node-22", "", "ünïcode"]
+    dims = 3
+    vec = np.arange(len(ids) * dims, dtype="<f4")
+    blob = struct.pack("<II", dims, len(ids))
+    for s in ids:
+        b = s.encode("utf-8")
+        blob += struct.pack("<I", len(b)) + b
+    off = len(blob)
+    blob += vec.tobytes()
+    assert blob_vectors(blob) == (dims, len(ids), off)
+    assert off % 4 != 0  # the payload really is unaligned in this example
+    for bad in (blob[:7], blob[:off - 3], blob[:-1]):
+        with pytest.raises(KnnError):
+            blob_vectors(bad)

@@ -93,6 +93,41 @@ def test_serialize_roundtrip(knn_lib, oracle_mod):
     ei.Release(); other.Release()
 
 
+def test_cold_start_feed_large_unaligned_blob_and_fp16_conversion(knn_lib, oracle_mod):
+    """a serialized index whose fp32 payload starts at an odd byte offset and spans several 32 MB staging
+    chunks loads bit-exactly through the pinned double buffer; an fp16 index converts on the device while loading."""
+    import struct
+    import time
+    from nornicdb_b200.embedding_index import EmbeddingIndex
+    n, d = 70_000, 384  # 107 MB of vectors: 4 staging chunks
+    rows = oracle_mod.fill_uniform(n, d, 77)
+    ids = [f"n{i}" for i in range(n)]
+    blob = bytearray(struct.pack("<II", d, n))
+    for s in ids:
+        b = s.encode()
+        blob += struct.pack("<I", len(b)) + b
+    assert len(blob) % 4 != 0
+    blob += rows.tobytes()
+    blob = bytes(blob)
+    ei = EmbeddingIndex(d)
+    t0 = time.perf_counter()
+    ei.Deserialize(blob)
+    dt = time.perf_counter() - t0
+    assert ei.Count() == n and ei.nodeIDs[-1] == ids[-1]
+    for r in (0, 21_845, 43_690, n - 1):  # rows around the chunk boundaries
+        assert ei._ix.read_rows(r, 1).tobytes() == rows[r:r + 1].tobytes()
+    assert ei.Serialize() == blob
+    q = oracle_mod.fill_uniform(1, d, 5)[0]
+    want = [r.ID for r in ei.Search(q, 10)]
+    h = EmbeddingIndex(d, dtype="f16")
+    h.Deserialize(blob)  # fp32 blob -> fp16 rows, converted on the device
+    assert h._ix.read_rows(12_345, 3).tobytes() == rows[12_345:12_348].astype(np.float16).tobytes()
+    got = [r.ID for r in h.Search(q, 10)]
+    assert len(set(got) & set(want)) >= 9  # fp16 rows: at most a boundary swap
+    print(f"cold-start feed: {len(blob) / dt / 1e9:.2f} GB/s through Deserialize (ids parsed on the host)")
+    ei.Release(); h.Release()
+
+
 def test_search_batch_uses_one_fused_call(knn_lib, oracle_mod):
     from nornicdb_b200.embedding_index import EmbeddingIndex
     rows = oracle_mod.fill_uniform(3000, 64, 3)
