@@ -141,6 +141,11 @@ int nk_index_update_row(NkIndex *ix, uint64_t row, const void *row_host);
 /* Swap-with-last removal (EmbeddingIndex.Remove, gpu.go:1437-1471): row `row` takes the contents of the
  * last row and the corpus shrinks by one. */
 int nk_index_remove_swap(NkIndex *ix, uint64_t row);
+/* Row filter for subsequent searches — the label / type filter of db.index.vector.queryNodes (call_vector.go:177-193) as
+ * a row bitmask, also usable for tombstones: bit r of mask_words (LSB first in 32-bit words, n_bits = rows of the index)
+ * set = row r may be returned; k is clamped to the number of set bits.  NULL clears the filter.  Honoured inside every
+ * scan kernel (no over-fetch).  upload / append / remove_swap / fill / attach clear it. */
+int nk_index_set_row_mask(NkIndex *ix, const uint32_t *mask_words, uint64_t n_bits);
 /* Fill the index with n_rows synthetic rows generated ON DEVICE by the counter-based generator shared
  * with the oracle (oracle/knn_oracle.c orc_fill_uniform): U[-1,1), element (r,j) depends only on
  * (seed, r, j).  Used by bench.py and the large-shape tests so 40 GB corpora never cross PCIe. */

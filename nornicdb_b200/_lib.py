@@ -76,6 +76,7 @@ SIGNATURES = {
     "nk_search_keys_device": (_i, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp]),
     "nk_merge_keys_device": (_i, [_i, _vp, C.c_uint32, C.c_uint32, C.c_uint32, _i, _vp, _vp, _vp]),
     "nk_score_subset": (_i, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp]),
+    "nk_index_set_row_mask": (_i, [_vp, _vp, _u64]),
     "nk_index_upload_from_f32": (_i, [_vp, _vp, _u64]),
     "nk_blob_vectors": (_i, [_vp, C.c_size_t, _vp, _vp, _vp]),
     "nk_index_assign_nearest": (_i, [_vp, _vp, C.c_uint32, _i, _vp, _vp]),

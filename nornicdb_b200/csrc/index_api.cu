@@ -43,6 +43,9 @@ struct NkShard {
     void *stage[2] = {nullptr, nullptr};
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     void *cvt = nullptr;  // device scratch for fp32 -> fp16 conversion at load
+    uint32_t *mask = nullptr;  // optional row filter (nk_index_set_row_mask): bit = local row
+    size_t mask_bytes = 0;
+    bool mask_on = false;
     size_t cvt_bytes = 0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // pending scan-kernel event pairs
     std::vector<uint64_t> timing_launches;
@@ -58,6 +61,8 @@ struct NkIndex {
     int last_path = NK_PATH_SIMT;
     uint64_t row_base = 0;
     std::vector<NkShard> shards;
+    uint64_t mask_alive = 0;  // rows that pass the row mask (all shards); meaningful while a mask is set
+    bool mask_on = false;
     NkStats stats{};
     std::mutex mu;
     size_t esz() const { return dtype == NK_DTYPE_F16 ? 2 : 4; }
@@ -68,6 +73,12 @@ struct NkIndex {
         return t;
     }
 };
+
+// Row-count changing mutations invalidate the row mask (its bits are positions).
+static void drop_row_mask(NkIndex *ix) {
+    ix->mask_on = false;
+    for (auto &s : ix->shards) s.mask_on = false;
+}
 
 static void shard_drop_shadow(NkShard &s) {
     if (s.shadow) cudaFree(s.shadow);
@@ -221,6 +232,7 @@ static int run_scan_bigk(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q
         a.rows = custom_rows ? rows : s.rows; a.dtype = ix->dtype; a.n = custom_rows ? n_rows : (uint32_t)s.n; a.dim = ix->dim;
         a.row_base = custom_rows ? 0 : s.base;
         a.queries = q_dev; a.Q = Q; a.k = kp; a.metric = ix->metric; a.stream = stream; a.below = s.ws.below;
+        a.row_mask = (!custom_rows && s.mask_on) ? s.mask : nullptr;
         if (nk::scan_simt(s.di, a, s.ws, s.ws.keys2, &ix->stats.kernel_launches)) return -1;
         NK_CUDA_OK(cudaMemcpy2DAsync(out_keys + done, (size_t)k * 8, s.ws.keys2, (size_t)kp * 8, (size_t)kp * 8, Q,
                                      cudaMemcpyDeviceToDevice, stream));
@@ -239,6 +251,7 @@ static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uin
     nk::ScanArgs a;
     a.rows = s.rows; a.dtype = ix->dtype; a.n = (uint32_t)s.n; a.dim = ix->dim; a.row_base = s.base;
     a.queries = q_dev; a.Q = Q; a.k = k; a.metric = ix->metric; a.stream = stream;
+    a.row_mask = s.mask_on ? s.mask : nullptr;
     // AUTO (measured on B200, N=10M d=1024, ms per batch).  fp32 rows: CUDA-core scan 5.9 / 6.2 / 6.1 / 7.6 at Q = 1 / 2 /
     // 4 / 8, TF32 tensor filter 5.8 for any Q <= 64 -> CUDA cores keep Q <= 4, tensor cores from 5 queries on.  With a
     // BF16 shadow the filter streams half the bytes: 2.9-3.1 ms for any Q <= 128, so it serves every batch size once the
@@ -348,6 +361,7 @@ void nk_index_release(NkIndex *ix) {
             if (s.stage_ev[i]) cudaEventDestroy(s.stage_ev[i]);
         }
         if (s.cvt) cudaFree(s.cvt);
+        if (s.mask) cudaFree(s.mask);
         s.ws.release();
     }
     delete ix;
@@ -357,6 +371,7 @@ static int upload_impl(NkIndex *ix, const void *rows_host, uint64_t n_rows, bool
     if (!ix) { nk::set_error("null index"); return -1; }
     if (n_rows && !rows_host) { nk::set_error("null rows"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
+    drop_row_mask(ix);
     const bool cvt = src_is_f32 && ix->dtype == NK_DTYPE_F16;
     const size_t rb = (size_t)ix->dim * ix->esz(), src_rb = (size_t)ix->dim * (cvt ? 4 : ix->esz());
     const uint64_t G = ix->shards.size();
@@ -415,6 +430,7 @@ int nk_index_append(NkIndex *ix, const void *rows_host, uint64_t n_rows) {
     if (n_rows == 0) return 0;
     if (!rows_host) { nk::set_error("null rows"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
+    drop_row_mask(ix);
     NkShard &s = ix->shards.back();
     const size_t rb = (size_t)ix->dim * ix->esz();
     if (s.n + n_rows > 0xfffffff0ull) { nk::set_error("shard exceeds 2^32 rows"); return -1; }
@@ -449,6 +465,7 @@ int nk_index_remove_swap(NkIndex *ix, uint64_t row) {
     std::lock_guard<std::mutex> lk(ix->mu);
     uint64_t total = ix->rows();
     if (row >= total) { nk::set_error("row %llu out of range", (unsigned long long)row); return -1; }
+    drop_row_mask(ix);
     // last non-empty shard holds the last row
     NkShard *last = nullptr;
     for (auto it = ix->shards.rbegin(); it != ix->shards.rend(); ++it)
@@ -473,6 +490,7 @@ int nk_index_remove_swap(NkIndex *ix, uint64_t row) {
 int nk_index_fill_uniform(NkIndex *ix, uint64_t n_rows, uint64_t seed) {
     if (!ix) { nk::set_error("null index"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
+    drop_row_mask(ix);
     const uint64_t G = ix->shards.size();
     if (n_rows / G + 1 > 0xfffffff0ull) { nk::set_error("shard exceeds 2^32 rows"); return -1; }
     uint64_t off = 0;
@@ -516,8 +534,44 @@ int nk_index_attach_device_rows(NkIndex *ix, void *rows_dev, uint64_t n_rows) {
     NK_CUDA_OK(cudaSetDevice(s.device));
     if (s.rows && s.owns) NK_CUDA_OK(cudaFree(s.rows));
     shard_drop_shadow(s);  // caller-owned rows may change behind the library's back: no shadow
+    drop_row_mask(ix);
     s.rows = rows_dev; s.owns = false; s.n = n_rows; s.cap = n_rows;
     rebase(ix);
+    return 0;
+}
+
+// Row filter for subsequent searches (label / type filter of db.index.vector.queryNodes, call_vector.go:177-193; also
+// tombstones): bit r of mask_words (LSB first in 32-bit words) set = row r (relative to the index's first row) may be
+// returned.  NULL clears the filter.  Row-count changing mutations (upload, append, remove_swap, fill, attach) clear it.
+int nk_index_set_row_mask(NkIndex *ix, const uint32_t *mask_words, uint64_t n_bits) {
+    if (!ix) { nk::set_error("null index"); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (!mask_words) {
+        drop_row_mask(ix);
+        return 0;
+    }
+    if (n_bits != ix->rows()) { nk::set_error("row mask has %llu bits, index has %llu rows", (unsigned long long)n_bits, (unsigned long long)ix->rows()); return -1; }
+    uint64_t off = 0, alive = 0;
+    std::vector<uint32_t> local;
+    for (auto &s : ix->shards) {
+        const size_t words = (size_t)((s.n + 31) / 32);
+        local.assign(words ? words : 1, 0u);
+        for (uint64_t r = 0; r < s.n; ++r) {
+            const uint64_t g = off + r;
+            if ((mask_words[g >> 5] >> (g & 31)) & 1u) {
+                local[r >> 5] |= 1u << (r & 31);
+                ++alive;
+            }
+        }
+        NK_CUDA_OK(cudaSetDevice(s.device));
+        if (nk::ws_reserve((void **)&s.mask, &s.mask_bytes, local.size() * 4)) return -1;
+        NK_CUDA_OK(cudaMemcpyAsync(s.mask, local.data(), local.size() * 4, cudaMemcpyHostToDevice, s.stream));
+        NK_CUDA_OK(cudaStreamSynchronize(s.stream));
+        s.mask_on = true;
+        off += s.n;
+    }
+    ix->mask_on = true;
+    ix->mask_alive = alive;
     return 0;
 }
 
@@ -611,7 +665,7 @@ static int check_flags(NkShard &s) {
 int nk_search(NkIndex *ix, const float *queries_host, uint32_t Q, uint32_t k, uint32_t *out_idx, float *out_score) {
     if (!ix) { nk::set_error("null index"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
-    const uint64_t N = ix->rows();
+    const uint64_t N = ix->mask_on ? ix->mask_alive : ix->rows();  // rows that can be returned
     if (k == 0 || N == 0 || Q == 0) return 0;  // cuda_bridge.go:644-646, gpu.go:1540-1542
     if (!queries_host || !out_idx || !out_score) { nk::set_error("null argument"); return -1; }
     const uint32_t ke = k > N ? (uint32_t)N : k;  // cuda_bridge.go:647-649

@@ -50,6 +50,9 @@ struct ScanArgs {
     // k > NK_MAX_K is served by repeated passes: pass p only admits keys strictly below below[q] (the last key the
     // previous pass returned for query q); nullptr = no bound.  CUDA-core scan only.
     const uint64_t *below = nullptr;
+    // optional row filter (label / tombstone bitmask): bit r (LSB first in 32-bit words) set = local row r takes part;
+    // nullptr = every row.  Honoured by every scan kernel.
+    const uint32_t *row_mask = nullptr;
     // optional BF16 shadow of an fp32 shard (scan_tensor_shadow.cu): rows of `shadow_dimpad` bf16 + per-row |x|^2 and
     // |x - bf16(x)|^2; nullptr = none
     const void *shadow = nullptr;

@@ -38,6 +38,7 @@ struct SimtParams {
     int *flags;
     const int *only_if;  // device-side conditional fallback: run only if *only_if != 0
     const uint64_t *below;  // per-query exclusive key bound (k > NK_MAX_K passes) or nullptr
+    const uint32_t *mask;   // row bitmask or nullptr
 };
 
 // ---- element loaders -------------------------------------------------------------------------
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) knn_scan_simt_kernel(SimtParams 
                 xr = __shfl_sync(0xffffffffu, xx[0], r * (32 / R));
             }
             const uint32_t row = row0 + r;
-            if ((lane % LPV) == 0 && row < n && (uint32_t)qi < p.nq) {
+            if ((lane % LPV) == 0 && row < n && (uint32_t)qi < p.nq && (!p.mask || ((p.mask[row >> 5] >> (row & 31)) & 1u))) {
                 if constexpr (EUCLID) {
                     s = -s;
                 } else if (p.metric == NK_METRIC_COSINE) {
@@ -331,7 +332,7 @@ int scan_simt(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *
         SimtParams p;
         p.rows = a.rows; p.n = a.n; p.dim = a.dim; p.row_base = a.row_base;
         p.queries = a.queries; p.q0 = q0; p.nq = left < (uint32_t)qt ? left : (uint32_t)qt; p.k = a.k;
-        p.metric = a.metric; p.P = P; p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = a.only_if; p.below = a.below;
+        p.metric = a.metric; p.P = P; p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = a.only_if; p.below = a.below; p.mask = a.row_mask;
         kern<<<grid_used, SIMT_THREADS, smem, a.stream>>>(p);
         NK_CUDA_OK(cudaGetLastError());
         if (launches) ++*launches;

@@ -299,6 +299,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
             for (uint32_t m = 0; m < 2; ++m) {
                 const uint32_t rt = m * 128 + quad * 32 + lane;
                 const uint32_t row = tile * ROWS + rt;
+                const bool alive = row < p.n && (!p.mask || ((__ldg(p.mask + (row >> 5)) >> (row & 31)) & 1u));
                 { TC_PROF_BEGIN(); ptx::mbar_wait(&sh.accfull[m], it & 1); TC_PROF_END(a); }
                 ptx::tc_fence_after();
                 // score(row, query c):
@@ -312,7 +313,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                 if (cosine) mul = x2 > 0.0f ? 1.0f / xn : 0.0f;
                 if (FILTER) {
                     bnd = cosine ? p.margin_c : bfac * xn;
-                    if (!cosine && row < p.n) atomicMax(&sh.maxxx, __float_as_uint(x2));
+                    if (!cosine && alive) atomicMax(&sh.maxxx, __float_as_uint(x2));
                     if (euclid) mul = 2.0f;
                 }
 #pragma unroll 1
@@ -348,12 +349,12 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                                 } else if (sc != sc) {
                                     sc = -INFINITY;
                                 }
-                                my_cand[(size_t)qi * P + slot] = row < p.n ? make_key(sc, grow) : 0ull;  // 0 = empty slot
+                                my_cand[(size_t)qi * P + slot] = alive ? make_key(sc, grow) : 0ull;  // 0 = empty slot
                             }
                         }
                         if (rt == 0 && half == 0)
                             for (uint32_t qi = m == 0 ? 0 : nq; qi < nq; ++qi) sh.cnt[qi] = (int)((it + 1) * ROWS);
-                    } else if (row < p.n && cb < nq) {
+                    } else if (alive && cb < nq) {
                         // Compact compare pass -> 64-bit mask of columns worth buffering (NaN passes); the rare pushes
                         // run in a small out-of-line loop so the hot code stays a few hundred instructions (a fully
                         // unrolled push per column was ~40 KB of SASS: I-cache thrash).
@@ -741,7 +742,7 @@ static int launch_pass(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
     p.n = a.n; p.dim = a.dim; p.nslab = (a.dim + BK - 1) / BK; p.row_base = a.row_base;
     p.q0 = q0; p.nq = nq; p.k = a.k; p.qpad_off = q0; p.qgroups = qgroups; p.list_cap = grid * k_emit;
     p.metric = a.metric; p.k_emit = k_emit; p.margin_c = margin_c; p.qnorm = qnorm;
-    p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = only_if; p.debug = tc_debug_flags();
+    p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = only_if; p.debug = tc_debug_flags(); p.mask = a.row_mask;
     p.gtau = reinterpret_cast<uint32_t *>(ws.keys2); p.gcount = reinterpret_cast<int *>(ws.keys2) + (Qpad + QT_BIG);
     knn_scan_tc_kernel<NT, QT><<<grid, THREADS, smem, a.stream>>>(map_rows, map_qhi, map_qlo, p);
     NK_CUDA_OK(cudaGetLastError());

@@ -275,6 +275,7 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
         for (uint32_t tile = sub; tile < num_tiles; tile += sgrid, ++it) {
             const uint32_t buf = it & 1;
             const uint32_t row = tile * ROWS + rt;
+            const bool alive = row < p.n && (!p.mask || ((__ldg(p.mask + (row >> 5)) >> (row & 31)) & 1u));
             // the buffered key is the UPPER bound of the score, bound(row, q) = ra qa[q] + rb qb[q]:
             //   cosine     acc/|x|                        ra = |dx|/|x|   rb = 1
             //   dot        acc                            ra = |dx|       rb = |x|
@@ -290,7 +291,7 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
             } else if (euclid) {
                 mul = 2.0f; ra = 2.0f * dxn; rb = 2.0f * xn;
             }
-            if (row < p.n && ra < INFINITY && rb < INFINITY) {  // NaN / Inf rows are kept anyway (score NaN -> +inf below)
+            if (alive && ra < INFINITY && rb < INFINITY) {  // NaN / Inf rows are kept anyway (score NaN -> +inf below)
                 atomicMax(&sh.max_ra, __float_as_uint(ra));
                 if (!cosine) { atomicMax(&sh.max_rb, __float_as_uint(rb)); atomicMax(&sh.maxxx, __float_as_uint(x2)); }
             }
@@ -320,12 +321,12 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
                             float sc = fmaf(__uint_as_float(c < 32 ? v0[c & 31] : v1[c & 31]), mul, fmaf(ra, sh.qa[qi], rb * sh.qb[qi]));
                             if (euclid) { const float qn = sh.qn[qi]; sc -= EUC_KEEP * fmaf(qn, qn, x2); }
                             if (sc != sc) sc = INFINITY;
-                            my_cand[(size_t)qi * P + slot] = row < p.n ? make_key(sc, grow) : 0ull;  // 0 = empty slot
+                            my_cand[(size_t)qi * P + slot] = alive ? make_key(sc, grow) : 0ull;  // 0 = empty slot
                         }
                     }
                     if (rt == 0 && chunk == 0)
                         for (uint32_t qi = 0; qi < nq; ++qi) sh.cnt[qi] = (int)((it + 1) * ROWS);
-                } else if (row < p.n && cb < nq) {
+                } else if (alive && cb < nq) {
                     // compact compare pass -> 64-bit mask of columns worth buffering (NaN passes); rare pushes out of line
                     uint32_t pass0 = 0, pass1 = 0;
 #pragma unroll
@@ -448,7 +449,7 @@ static int launch_shadow_pass_t(const DeviceInfo &di, const ScanArgs &a, Workspa
     p.q0 = q0; p.nq = nq; p.k = a.k; p.qpad_off = q0; p.qgroups = qgroups; p.list_cap = grid * k_emit;
     p.metric = a.metric; p.k_emit = k_emit; p.margin_c = 0.0f; p.qnorm = qnorm; p.qa = qa; p.qb = qb;
     p.xnorm2 = a.xnorm2; p.dnorm2 = a.dnorm2;
-    p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = nullptr; p.debug = tc_debug_flags();
+    p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = nullptr; p.debug = tc_debug_flags(); p.mask = a.row_mask;
     p.gtau = reinterpret_cast<uint32_t *>(ws.keys2); p.gcount = reinterpret_cast<int *>(ws.keys2) + (Qpad + QT_BIG);
     knn_scan_shadow_kernel<QT><<<grid, NTHREADS, smem, a.stream>>>(map_rows, map_q, p);
     NK_CUDA_OK(cudaGetLastError());

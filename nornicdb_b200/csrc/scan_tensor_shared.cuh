@@ -38,6 +38,7 @@ struct Params {
     int *flags;               // [0] fatal buffer overflow, [1] filter-margin overflow (-> next stage), [2] max |x|^2 bits,
                               // [4] / [6] BF16 max ra / rb bits, [5] retry-stage marker, [7] longest list (diagnostics)
     const int *only_if;       // exact fallback: run only if *only_if != 0
+    const uint32_t *mask;     // row bitmask (bit set = row takes part) or nullptr
     int debug;                // NK_TC_DEBUG bit 64: clock64 wait-time instrumentation of CTA 0
 };
 }  // namespace tc

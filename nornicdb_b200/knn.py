@@ -77,6 +77,18 @@ class KnnIndex:
             ptr, n_rows = a.ctypes.data, a.shape[0]
         _check(self.lib.nk_index_upload_from_f32(self.ptr, C.c_void_p(ptr), int(n_rows)), "nk_index_upload_from_f32")
 
+    def set_row_mask(self, keep) -> None:
+        """Row filter for the following searches: `keep` = boolean array with one entry per row (True = may be returned),
+        or None to clear.  (Label filter of queryNodes, call_vector.go:177-193, evaluated inside the scan kernels.)"""
+        if keep is None:
+            _check(self.lib.nk_index_set_row_mask(self.ptr, None, 0), "nk_index_set_row_mask")
+            return
+        b = np.asarray(keep, dtype=bool).reshape(-1)
+        words = np.packbits(b, bitorder="little")
+        words = np.concatenate([words, np.zeros((-len(words)) % 4, dtype=np.uint8)]).view("<u4")
+        words = np.ascontiguousarray(words)
+        _check(self.lib.nk_index_set_row_mask(self.ptr, words.ctypes.data_as(C.c_void_p), int(b.size)), "nk_index_set_row_mask")
+
     def append(self, rows) -> None:
         a = self._rows(rows)
         _check(self.lib.nk_index_append(self.ptr, a.ctypes.data_as(C.c_void_p), a.shape[0]), "nk_index_append")

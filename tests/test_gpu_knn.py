@@ -327,3 +327,41 @@ def test_multi_device_index_in_one_process(knn_lib, oracle_mod):
     ix.fill_uniform(n, 42)  # device-side generation is shard-aware: same global stream
     assert (ix.read_rows(0, n) == rows).all()
     ix.release()
+
+
+@pytest.mark.parametrize("path,Q", [("simt", 3), ("shadow", 40), ("filter", 40), ("tensor", 40), ("auto", 300)])
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_row_mask_filters_inside_every_kernel(knn_lib, oracle_mod, path, Q, metric):
+    """nk_index_set_row_mask (label filter of queryNodes, call_vector.go:177-193): masked search == search over the kept rows."""
+    from nornicdb_b200.knn import KnnIndex
+    if path == "tensor" and metric == "euclidean":
+        pytest.skip("exact 3xTF32 path: cosine / dot only")
+    n, d, k = 7_000, 64, 10
+    rows = oracle_mod.fill_uniform(n, d, 11)
+    q = oracle_mod.fill_uniform(Q, d, 12)
+    keep = np.random.default_rng(4).random(n) < 0.3
+    keep[:40] = False
+    ix = KnnIndex(d, metric=metric)
+    ix.upload(rows)
+    ix.set_path(path)
+    ix.set_row_mask(keep)
+    gi, gs = ix.search(q, k)
+    kept = np.nonzero(keep)[0]
+    oi, os_ = oracle_mod.knn_exact64(rows[kept], q, k, metric)
+    check_parity(rows, q, k, metric, gi, gs, kept[oi].astype(np.uint32), os_)
+    assert keep[gi].all()
+    # fewer kept rows than k: k is clamped to the number of set bits
+    few = np.zeros(n, dtype=bool)
+    few[[5, 77, 6_999]] = True
+    ix.set_row_mask(few)
+    gi, gs = ix.search(q[:2], k)
+    assert gi.shape == (2, 3) and sorted(gi[0].tolist()) == [5, 77, 6_999]
+    ix.set_row_mask(None)  # cleared: the full corpus again
+    gi, gs = ix.search(q, k)
+    oi, os_ = oracle_mod.knn_exact64(rows, q, k, metric)
+    check_parity(rows, q, k, metric, gi, gs, oi, os_)
+    ix.set_row_mask(keep)
+    ix.append(rows[:3])    # a row-count change drops the mask
+    gi, _ = ix.search(q[:1], k)
+    assert gi.shape == (1, k)
+    ix.release()
