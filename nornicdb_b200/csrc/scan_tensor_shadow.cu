@@ -347,12 +347,16 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
                     while (pass) {
                         const uint32_t c = (uint32_t)__ffsll((long long)pass) - 1u;
                         pass &= pass - 1ull;
-                        uint32_t bits = 0;
+                        // the register file is not indexable: a 6-level select tree (63 SEL) picks column c
+                        uint32_t t[32];
 #pragma unroll
-                        for (uint32_t i = 0; i < 32; ++i) {  // register file is not indexable: select by compare
-                            if (c == i) bits = v0[i];
-                            if (c == 32 + i) bits = v1[i];
+                        for (int i = 0; i < 32; ++i) t[i] = (c & 32u) ? v1[i] : v0[i];
+#pragma unroll
+                        for (int w = 16; w >= 1; w >>= 1) {
+#pragma unroll
+                            for (int i = 0; i < w; ++i) t[i] = (c & (uint32_t)w) ? t[i + w] : t[i];
                         }
+                        const uint32_t bits = t[0];
                         const uint32_t qi = cb + c;
                         float sc = fmaf(__uint_as_float(bits), mul, fmaf(ra, sh.qa[qi], rb * sh.qb[qi]));
                         if (euclid) { const float qn = sh.qn[qi]; sc -= EUC_KEEP * fmaf(qn, qn, x2); }

@@ -14,7 +14,7 @@ constexpr int TMEM_COLS = 512;
 constexpr int EPI_THREADS = 128;
 constexpr int EPI_BAR = 1;
 constexpr int P = 512;           // candidate buffer capacity per (CTA, query): warp_prune<16>
-constexpr int QT_BIG = 256;      // most query columns any kernel serves per CTA (workspace sizing)
+constexpr int QT_BIG = 256;      // padding of the per-query arrays (a CTA reads up to 128 entries past the last query)
 constexpr float EUC_EPS = 4e-6f;  // fp32 rounding of |x|^2 + |q|^2 in the euclidean upper bound
 constexpr float EUC_KEEP = 1.0f - EUC_EPS;
 
