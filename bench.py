@@ -429,6 +429,12 @@ def main():
                 "algorithmic_bytes_per_launch": algo_bytes_per_launch,
                 "avg_launch_ms": avg_launch_ms, "scan_launches_per_step": scan_kernel_launches / args.steps,
                 "scan_share_of_step": scan_ms / sum(step_ms)}
+    if used_path == "shadow":
+        roofline["note"] = ("the scan streams the BF16 shadow (n*dpad*2 + 8n bytes per launch), not the fp32 rows: `achieved` counts the "
+                            "bytes actually read; SURVEY.md 8(d)'s fp32 figure n*d*4 is reported as fp32_equivalent_gbs for comparison "
+                            "with the --path filter / simt scans, which do read the fp32 rows")
+        roofline["fp32_corpus_bytes_per_launch"] = n_shard * dim * elem
+        roofline["fp32_equivalent_gbs"] = n_shard * dim * elem / (avg_launch_ms / 1e3) / 1e9
     if used_path in ("tensor", "filter", "shadow"):
         # roofline fraction = max(bytes/t / BW, flops/t / tensor peak).  Large batches (several query
         # blocks per corpus pass) are bound by the tensor pipes, not by HBM: report whichever bound is tighter.
