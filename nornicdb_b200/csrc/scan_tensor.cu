@@ -1,4 +1,6 @@
-// scan_tensor.cu — fused distance + top-k scan on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+// scan_tensor.cu — fused distance + top-k scan over the FP32 rows on the 5th-gen tensor cores (tcgen05 + TMEM + TMA):
+// the path of shards without a BF16 shadow, the retry stage of the shadow filter (scan_tensor_shadow.cu), the exact
+// 3xTF32 scan, plus the finish step and the host logic both filters share.
 //
 // For Q > ~16 queries the CUDA-core scan stops being HBM-bound (fp32 FMA ridge ~10 flop/byte, the batch needs
 // Q/2 flop/byte), so the Q x N^T contraction moves to tcgen05.mma.  fp32 inputs on tensor cores mean TF32
@@ -28,7 +30,9 @@
 //   warps 12-15 epilogue: tcgen05.ld the [128 rows x 64 queries] accumulator (thread = corpus row), release it,
 //               scale / bound, compare against each query's running threshold with a compact mask pass, append the
 //               few survivors; warp-level register top-k prune.  Distances never go to memory.
-// Per-CTA lists are folded by merge_keys().
+// Exact mode: per-CTA lists are folded by merge_keys().  Filter mode: CTAs share their thresholds through a per-query
+// atomic max, append their survivors to one list per query, and filter_finish_kernel (below) selects, re-scores and
+// sorts.  Large batches: 2 / 4 query groups per launch share every corpus tile through L2 (Params::qgroups).
 //
 // Algorithmic HBM traffic per launch: n*dim*4 (corpus, once); query re-reads are served from L2.
 #include <cuda.h>
