@@ -878,7 +878,7 @@ int nk_score_subset(NkIndex *ix, const float *query_host, const uint32_t *rows_h
 
 // ---- k-means routing on device (pkg/gpu/kmeans.go) -----------------------------------------------
 // Assignment is the fused scan with the roles swapped: the K centroids are the indexed corpus, the shard's rows are the
-// queries — read in place from HBM, 1024 at a time — and k = 1.  Ties go to the lowest centroid index (strict < / >
+// queries — read in place from HBM, 8192 at a time — and k = 1.  Ties go to the lowest centroid index (strict < / >
 // in kmeans.go:470-476,529-534).
 int nk_index_assign_nearest(NkIndex *ix, const float *centroids_host, uint32_t K, int metric, int32_t *assign_io, uint64_t *changed) {
     if (!ix || !centroids_host || !assign_io) { nk::set_error("null argument"); return -1; }
@@ -907,7 +907,7 @@ int nk_index_assign_nearest(NkIndex *ix, const float *centroids_host, uint32_t K
             if (e == cudaSuccess) e = cudaMemcpyAsync(d_prev, assign_io + off, s.n * 4, cudaMemcpyHostToDevice, s.stream);
             if (e != cudaSuccess) rc = -1;
         }
-        const uint64_t B = 1024;
+        const uint64_t B = 8192;  // rows per fused search: amortises the ~12 fixed launches of a search over 8 scan launches
         for (uint64_t b = 0; rc == 0 && b < s.n; b += B) {
             const uint32_t nb = (uint32_t)std::min<uint64_t>(B, s.n - b);
             if (nk_search_device(cx, static_cast<const float *>(s.rows) + b * ix->dim, nb, 1, d_idx + b, d_sc + b, s.stream) < 0) rc = -1;
