@@ -21,6 +21,10 @@ bool scan_tensor_supported(const DeviceInfo &di, const ScanArgs &a);
 int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *out_keys, uint64_t *launches);
 bool scan_tensor_filter_supported(const DeviceInfo &di, const ScanArgs &a);
 bool shadow_pass_supported(const DeviceInfo &di, const ScanArgs &a);
+bool assign_tensor_supported(const DeviceInfo &di, uint32_t dim, uint32_t K, int metric);
+int assign_tensor(const DeviceInfo &di, const float *rows, const void *shadow, uint32_t dimpad, const float *xnorm2, const float *dnorm2,
+                  uint32_t n, uint32_t dim, const float *centroids_dev, uint32_t K, int metric, uint32_t *assign_dev, cudaStream_t stream,
+                  uint64_t *launches);
 int build_shadow(const float *rows, uint64_t first, uint64_t count, uint32_t dim, uint32_t dimpad, void *shadow, float *xnorm2,
                  float *dnorm2, cudaStream_t stream);
 }
@@ -890,25 +894,34 @@ int nk_index_assign_nearest(NkIndex *ix, const float *centroids_host, uint32_t K
     for (auto &s : ix->shards) {
         if (s.n == 0) continue;
         NK_CUDA_OK(cudaSetDevice(s.device));
-        NkIndex *cx = nk_index_create(&s.device, 1, ix->dim, NK_DTYPE_F32, metric);
-        if (!cx) return -1;
+        // With a BF16 shadow the assignment is ONE pass of the tensor-core scan with an argmax epilogue (assign_tensor.cu);
+        // otherwise the fused kNN scan with the roles swapped: centroids as the corpus, rows as the queries, k = 1.
+        const bool tensor = s.shadow && s.shadow_n == s.n && nk::assign_tensor_supported(s.di, ix->dim, K, metric);
+        NkIndex *cx = tensor ? nullptr : nk_index_create(&s.device, 1, ix->dim, NK_DTYPE_F32, metric);
+        if (!tensor && !cx) return -1;
         uint32_t *d_idx = nullptr;
-        float *d_sc = nullptr;
+        float *d_sc = nullptr, *d_cen = nullptr;
         int32_t *d_prev = nullptr;
         unsigned long long *d_changed = nullptr, h_changed = 0;
-        int rc = nk_index_upload(cx, centroids_host, K);
+        int rc = tensor ? 0 : nk_index_upload(cx, centroids_host, K);
         cudaError_t e = cudaSuccess;
         if (rc == 0) {
             e = cudaMalloc((void **)&d_idx, s.n * 4);
             if (e == cudaSuccess) e = cudaMalloc((void **)&d_sc, s.n * 4);
             if (e == cudaSuccess) e = cudaMalloc((void **)&d_prev, s.n * 4);
             if (e == cudaSuccess) e = cudaMalloc((void **)&d_changed, 8);
+            if (e == cudaSuccess && tensor) e = cudaMalloc((void **)&d_cen, (size_t)K * ix->dim * 4);
+            if (e == cudaSuccess && tensor) e = cudaMemcpyAsync(d_cen, centroids_host, (size_t)K * ix->dim * 4, cudaMemcpyHostToDevice, s.stream);
             if (e == cudaSuccess) e = cudaMemsetAsync(d_changed, 0, 8, s.stream);
             if (e == cudaSuccess) e = cudaMemcpyAsync(d_prev, assign_io + off, s.n * 4, cudaMemcpyHostToDevice, s.stream);
             if (e != cudaSuccess) rc = -1;
         }
+        if (rc == 0 && tensor) {
+            rc = nk::assign_tensor(s.di, static_cast<const float *>(s.rows), s.shadow, ix->dimpad(), s.xnorm2, s.dnorm2, (uint32_t)s.n, ix->dim,
+                                   d_cen, K, metric, d_idx, s.stream, &ix->stats.kernel_launches);
+        }
         const uint64_t B = 8192;  // rows per fused search: amortises the ~12 fixed launches of a search over 8 scan launches
-        for (uint64_t b = 0; rc == 0 && b < s.n; b += B) {
+        for (uint64_t b = 0; rc == 0 && !tensor && b < s.n; b += B) {
             const uint32_t nb = (uint32_t)std::min<uint64_t>(B, s.n - b);
             if (nk_search_device(cx, static_cast<const float *>(s.rows) + b * ix->dim, nb, 1, d_idx + b, d_sc + b, s.stream) < 0) rc = -1;
         }
@@ -921,9 +934,9 @@ int nk_index_assign_nearest(NkIndex *ix, const float *centroids_host, uint32_t K
         }
         if (e != cudaSuccess) { nk::set_error("nk_index_assign_nearest: %s", cudaGetErrorString(e)); cudaGetLastError(); }
         cudaStreamSynchronize(s.stream);
-        cudaFree(d_idx); cudaFree(d_sc); cudaFree(d_prev); cudaFree(d_changed);
-        ix->stats.kernel_launches += cx->stats.kernel_launches + 1;
-        nk_index_release(cx);
+        cudaFree(d_idx); cudaFree(d_sc); cudaFree(d_prev); cudaFree(d_changed); cudaFree(d_cen);
+        ix->stats.kernel_launches += (cx ? cx->stats.kernel_launches : 0) + 1;
+        if (cx) nk_index_release(cx);
         if (rc != 0) return -1;
         total_changed += h_changed;
         off += s.n;

@@ -36,13 +36,20 @@ def _check_assign(rows, cen, got, want, by_cosine):
     return len(bad)
 
 
+@pytest.mark.parametrize("tensor", ["1", "0"])
 @pytest.mark.parametrize("metric", ["euclidean", "cosine"])
-@pytest.mark.parametrize("shape", [(20_000, 64, 37), (5_000, 128, 200), (3_000, 30, 5), (2_500, 256, 1)])
-def test_assign_nearest_matches_oracle(knn_lib, oracle_mod, metric, shape):
+@pytest.mark.parametrize("shape", [(20_000, 64, 37), (5_000, 128, 200), (3_000, 30, 5), (2_500, 256, 1), (12_000, 96, 600)])
+def test_assign_nearest_matches_oracle(knn_lib, oracle_mod, metric, shape, tensor, monkeypatch):
+    """tensor=1: one pass of the tensor-core scan with an argmax epilogue over the BF16 shadow (+ exact fp32 fix-up of
+    near-ties); tensor=0 (or no shadow / dim % 4 != 0): the fused kNN scan with the roles swapped."""
     from nornicdb_b200.knn import KnnIndex
+    monkeypatch.setenv("NK_ASSIGN_TENSOR", tensor)
     n, d, K = shape
     rows, mu = _mixture(n, d, max(K, 2), 5)
     cen = (mu[:K] + 0.01).astype(np.float32)
+    rows[11] = 0.0            # zero row: cosine 0 to every centroid -> centroid 0
+    if K > 3:
+        cen[3] = cen[1]       # duplicate centroid: exact tie, the lower index must win
     ix = KnnIndex(d, metric="cosine")
     ix.upload(rows)
     got = np.zeros(n, dtype=np.int32)
