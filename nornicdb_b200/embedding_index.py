@@ -4,7 +4,8 @@ Same method names / argument meaning / error behaviour as the Go type, so the te
 pkg/gpu/gpu_test.go.  Differences, all on purpose:
   * the device corpus is kept in step INCREMENTALLY (nk_index_append / update_row / remove_swap) — the
     reference marks gpuSynced=false on every mutation and re-uploads the whole corpus in syncToCUDA
-    (gpu.go:2088-2098); SyncToGPU() is therefore a no-op that reports success;
+    (gpu.go:2088-2098); SyncToGPU() has nothing to copy.  The OBSERVABLE state machine is kept (gpu_test.go:1403-1480):
+    Stats().GPUSynced / IsGPUSynced() turn false on Add / AddBatch / Remove / Clear / Deserialize and true on SyncToGPU();
   * rows stay raw on the device (cosine is computed in the kernel), so ScoreSubset is a device gather +
     fused scan, not a host gather + normalise + re-upload (gpu.go:1578-1589,1945);
   * there is no CPU fallback: without the CUDA library / a GPU every search raises.
@@ -56,6 +57,7 @@ class EmbeddingIndex:
         self._multi = len(devices) > 1
         self.mu = threading.RLock()
         self.searchesGPU = 0
+        self.gpuSynced = False  # gpu.go:1260: a fresh index is not synced
 
     # -- mutation ------------------------------------------------------------------------------------
     def _vec(self, embedding) -> np.ndarray:
@@ -67,6 +69,7 @@ class EmbeddingIndex:
     def Add(self, nodeID: str, embedding) -> None:  # gpu.go:1378-1403
         v = self._vec(embedding)
         with self.mu:
+            self.gpuSynced = False
             idx = self.idToIndex.get(nodeID)
             if idx is not None:
                 self._ix.update_row(idx, v)
@@ -80,6 +83,7 @@ class EmbeddingIndex:
             raise ValueError("gpu: nodeIDs and embeddings length mismatch")
         vecs = [self._vec(e) for e in embeddings]
         with self.mu:
+            self.gpuSynced = False
             fresh_ids, fresh = [], []
             pending: Dict[str, int] = {}
             for nid, v in zip(nodeIDs, vecs):
@@ -104,6 +108,7 @@ class EmbeddingIndex:
             if idx is None:
                 return False
             last = len(self.nodeIDs) - 1
+            self.gpuSynced = False
             self._ix.remove_swap(idx)
             if idx != last:
                 moved = self.nodeIDs[last]
@@ -118,6 +123,7 @@ class EmbeddingIndex:
             self._ix.upload(np.empty((0, self.dimensions), dtype=self._np_dtype))
             self.nodeIDs = []
             self.idToIndex = {}
+            self.gpuSynced = False
 
     def Release(self) -> None:
         with self.mu:
@@ -170,11 +176,12 @@ class EmbeddingIndex:
             return self._results(idx, sc)
 
     # -- bookkeeping ---------------------------------------------------------------------------------
-    def SyncToGPU(self) -> None:  # gpu.go:2025 — nothing to do: the device copy is always current
-        return None
+    def SyncToGPU(self) -> None:  # gpu.go:2025 — nothing to copy: the device rows are always current
+        with self.mu:
+            self.gpuSynced = True
 
     def IsGPUSynced(self) -> bool:
-        return True
+        return self.gpuSynced
 
     def Count(self) -> int:  # gpu.go:2225
         return len(self.nodeIDs)
@@ -196,7 +203,7 @@ class EmbeddingIndex:
 
     def Stats(self) -> EmbeddingIndexStats:  # gpu.go:2252-2276
         st = self._ix.stats()
-        return EmbeddingIndexStats(len(self.nodeIDs), self.dimensions, True, self.searchesGPU, 0,
+        return EmbeddingIndexStats(len(self.nodeIDs), self.dimensions, self.gpuSynced, self.searchesGPU, 0,
                                    st["searches"], st["bytes_h2d"])
 
     # -- checkpoint (gpu.go:2373-2454): LE [dims u32][count u32][len-prefixed ids...][float32 vectors...] ------
@@ -232,5 +239,6 @@ class EmbeddingIndex:
             # library's pinned double buffer; an fp16 index converts on the device while loading
             base = C.cast(C.c_char_p(data), C.c_void_p).value
             self._ix.upload_from_f32(ptr=base + voff, n_rows=count)
+            self.gpuSynced = False  # gpu.go:2452
             self.nodeIDs = ids
             self.idToIndex = {nid: i for i, nid in enumerate(ids)}

@@ -210,6 +210,7 @@ public:
     void Add(const std::string &nodeID, const std::vector<float> &embedding) {  // gpu.go:1378-1403
         if ((int)embedding.size() != dims_) throw ErrInvalidDimensions();
         std::lock_guard<std::mutex> lk(mu_);
+        gpuSynced_ = false;
         auto it = idToIndex_.find(nodeID);
         if (it != idToIndex_.end()) check(nk_index_update_row(ix_, it->second, embedding.data()));
         else {
@@ -227,6 +228,7 @@ public:
         auto it = idToIndex_.find(nodeID);
         if (it == idToIndex_.end()) return false;
         const uint64_t idx = it->second, last = nodeIDs_.size() - 1;
+        gpuSynced_ = false;
         check(nk_index_remove_swap(ix_, idx));
         if (idx != last) {
             nodeIDs_[idx] = nodeIDs_[last];
@@ -275,8 +277,10 @@ public:
         for (int i = 0; i < got; ++i) out.push_back({nodeIDs_[idx[i]], sc[i], 1.0f - sc[i]});
         return out;
     }
-    void SyncToGPU() {}  // gpu.go:2025: the device copy is always current
-    bool IsGPUSynced() const { return true; }
+    // gpu.go:2025: nothing to copy (the device rows are always current); the observable flag of gpu_test.go:1403-1480 is
+    // kept: false after Add / Remove / Deserialize, true after SyncToGPU
+    void SyncToGPU() { std::lock_guard<std::mutex> lk(mu_); gpuSynced_ = true; }
+    bool IsGPUSynced() const { return gpuSynced_; }
     int Count() const { return (int)nodeIDs_.size(); }                                   // gpu.go:2225
     bool Has(const std::string &id) const { return idToIndex_.count(id) != 0; }          // gpu.go:2279
     bool Get(const std::string &id, std::vector<float> *out) {                           // gpu.go:2287
@@ -315,6 +319,7 @@ public:
         }
         std::lock_guard<std::mutex> lk(mu_);
         check(nk_index_upload(ix_, data.data() + off, count));  // the blob streams straight into device memory
+        gpuSynced_ = false;
         nodeIDs_ = ids;
         idToIndex_.clear();
         for (uint32_t i = 0; i < count; ++i) idToIndex_[nodeIDs_[i]] = i;
@@ -326,6 +331,7 @@ private:
     NkIndex *ix_ = nullptr;
     std::vector<std::string> nodeIDs_;
     std::unordered_map<std::string, uint64_t> idToIndex_;
+    bool gpuSynced_ = false;
     std::mutex mu_;
 };
 

@@ -66,7 +66,7 @@ class FakeKnnIndex:
         return "fake"
 
     def stats(self):
-        return {"kernel_launches": self.searches, "searches": self.searches}
+        return {"kernel_launches": self.searches, "searches": self.searches, "bytes_h2d": 0, "bytes_d2h": 0}
 
     def search(self, queries, k):
         q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32))

@@ -42,7 +42,10 @@ def test_update_remove_has_get(knn_lib, oracle_mod):
     ei.AddBatch(ids[:150], rows[:150])
     for i in range(150, 200):
         ei.Add(ids[i], rows[i])
-    assert ei.Count() == 200 and ei.Has("n7") and not ei.Has("zz") and ei.IsGPUSynced()
+    assert ei.Count() == 200 and ei.Has("n7") and not ei.Has("zz")
+    assert not ei.IsGPUSynced() and not ei.Stats().GPUSynced   # "should not be synced after add" (gpu_test.go:1446-1454)
+    ei.SyncToGPU()
+    assert ei.IsGPUSynced() and ei.Stats().GPUSynced
     v, ok = ei.Get("n7")
     assert ok and (v == rows[7]).all()
     ei.Add("n7", rows[8] * 3.0)  # update in place -> now parallel to n8

@@ -35,6 +35,17 @@ def test_embedding_index_reference_cases(fake_device, kats):
             assert [r.ID for r in ei.ScoreSubset(t["query"], t["subset"])] == t["want_ids"]
     ei = EmbeddingIndex(4)
     assert ei.Search([1, 0, 0, 0], 3) is None            # empty index -> nil, nil (gpu.go:1540-1542)
+    # lifecycle of gpu_test.go:1403-1480: SyncToGPU sets GPUSynced, Add / Remove clear it, double Release is safe
+    life = EmbeddingIndex(4)
+    life.Add("a", [1, 0, 0, 0]); life.Add("b", [0, 1, 0, 0]); life.Add("c", [0.9, 0.1, 0, 0])
+    assert not life.Stats().GPUSynced
+    life.SyncToGPU()
+    assert life.Stats().GPUSynced and len(life.Search([1, 0, 0, 0], 2)) == 2
+    life.Add("d", [0, 0, 1, 0])
+    assert not life.Stats().GPUSynced
+    life.SyncToGPU(); life.Remove("d")
+    assert not life.IsGPUSynced()
+    life.Release(); life.Release()
     with pytest.raises(ErrInvalidDimensions):
         ei.Add("x", [1, 2, 3])
     ei.AddBatch(["a", "b", "c", "a"], [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]])  # duplicate id: last wins
