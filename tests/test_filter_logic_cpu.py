@@ -66,3 +66,38 @@ def test_filter_selection_returns_the_true_topk(case):
         want = np.array(sorted(range(n), key=lambda r: (-true_s[r], r))[:k])
         assert (got == want).all(), (case, trial, k, n_cta)
         assert n_cand < n / 4                       # and the filter does filter
+
+
+def test_assignment_candidate_rule_contains_the_true_nearest_centroid():
+    """assign_tensor.cu: a row keeps its 4 best UPPER bounds and its best LOWER bound over all centroids; the true winner
+    (highest true score, lowest index on ties) is always among {upper >= best lower}, and if the 4th best upper also
+    reaches the best lower bound the row must fall back to "all centroids"."""
+    rng = np.random.default_rng(5)
+    for trial in range(300):
+        K = int(rng.choice([1, 2, 3, 7, 64, 300]))
+        true_s = np.round(rng.standard_normal(K), int(rng.choice([1, 2, 6])))  # exact ties at low precision
+        B = rng.uniform(0.0, 0.3, K) if trial % 3 else np.full(K, 0.05)
+        err = rng.uniform(-1, 1, K) * B
+        if trial % 5 == 0:                          # adversarial: winner pushed down, the rest up
+            err = B.copy()
+            err[int(np.argmax(true_s))] = -B[int(np.argmax(true_s))]
+        approx = true_s + err
+        up, lo = approx + B, approx - B
+        top = []                                    # (upper, idx) kept sorted desc with strict insertion, like the kernel
+        for ci in range(K):
+            if len(top) < 4 or up[ci] > top[-1][0]:
+                top.append((up[ci], ci))
+                top.sort(key=lambda t: (-t[0], t[1]))
+                top = top[:4]
+        maxlo = lo.max()
+        want = int(min(np.flatnonzero(true_s == true_s.max())))
+        if len(top) == 4 and top[3][0] >= maxlo:
+            cands = list(range(K))                  # "ALL"
+        else:
+            cands = [ci for u, ci in top[:3] if u >= maxlo]
+        assert want in cands, (trial, K, want, cands)
+        decided = len(top) < 2 or not (top[1][0] >= maxlo)
+        if decided:
+            assert top[0][1] == want
+        got = min(cands, key=lambda ci: (-true_s[ci], ci))  # exact re-scoring in ascending order, strict comparison
+        assert got == want
