@@ -84,8 +84,10 @@ int cuda_topk(CudaDevice *dev, CudaBuffer *scores, unsigned int *out_indices, fl
 
 /* Metric enum = vectorspace.DistanceMetric, pkg/vectorspace/registry.go:27-31. */
 enum { NK_METRIC_COSINE = 0, NK_METRIC_DOT = 1, NK_METRIC_EUCLIDEAN = 2 };
-/* Corpus element type held in HBM.  Queries and scores are always fp32. */
-enum { NK_DTYPE_F32 = 0, NK_DTYPE_F16 = 1 };
+/* Corpus element type held in HBM.  Queries and scores are always fp32.  fp16 / bf16 corpora (SURVEY.md §8(f)3 "fp16/bf16
+ * down-conversion at load") are half the bytes; batches of >= 5 queries scan them IN PLACE on the tensor cores
+ * (tcgen05.mma.kind::f16 with fp16 or bf16 operands — no shadow copy, no row-side rounding residue). */
+enum { NK_DTYPE_F32 = 0, NK_DTYPE_F16 = 1, NK_DTYPE_BF16 = 2 };
 /* Kernel selection for nk_index_set_path (diagnostics / tests); AUTO picks by Q, dim and dtype. */
 /* TENSOR = exact 3xTF32 tensor-core scan; TENSOR_FILTER = 1xTF32 prefilter over the fp32 rows with rigorous margins +
  * exact fp32 rescoring (device-side fallback to the exact scan on margin overflow); TENSOR_SHADOW = the same filter
@@ -100,6 +102,9 @@ enum { NK_PATH_AUTO = 0, NK_PATH_SIMT = 1, NK_PATH_TENSOR = 2, NK_PATH_TENSOR_FI
 #define NK_MAX_K_TOTAL 65536u
 
 typedef struct NkIndex NkIndex;
+/* Exchange context of one rank of a row-sharded, one-rank-per-GPU search (see "Row-sharded search" below). */
+typedef struct NkComm NkComm;
+#define NK_COMM_HANDLE_BYTES 64 /* sizeof(cudaIpcMemHandle_t) */
 
 typedef struct NkStats {
     uint64_t rows;            /* total rows resident */
@@ -150,12 +155,31 @@ int nk_index_set_row_mask(NkIndex *ix, const uint32_t *mask_words, uint64_t n_bi
  * with the oracle (oracle/knn_oracle.c orc_fill_uniform): U[-1,1), element (r,j) depends only on
  * (seed, r, j).  Used by bench.py and the large-shape tests so 40 GB corpora never cross PCIe. */
 int nk_index_fill_uniform(NkIndex *ix, uint64_t n_rows, uint64_t seed);
+/* The Gaussian-mixture corpus of SURVEY.md §8(d) ("1000 centres, sigma = 0.1", the shape of cmd/kmeans-test-data's
+ * clusters mode, main.go:231-283), generated ON DEVICE: row r = centre[hash(r) % n_centres] + sigma * N(0,1) per element,
+ * centres U[-1,1)^dim.  unit_norm != 0 follows the reference tool to the letter (unit-length centres, rows normalised after
+ * the noise).  The near-tie stress case of the filter paths; device-only generator — tests read the rows back. */
+int nk_index_fill_clustered(NkIndex *ix, uint64_t n_rows, uint64_t seed, uint32_t n_centres, float sigma, int unit_norm);
 /* Single-device index only: this process owns rows [row_base, row_base+n) of a larger corpus
  * (multi-process sharding, one rank per GPU).  Emitted indices are global.  Also offsets the synthetic
  * generator so rank g's rows equal rows row_base.. of the global stream. */
 int nk_index_set_row_base(NkIndex *ix, uint64_t row_base);
-/* Adopt caller-owned device memory as the (single) shard; not freed by nk_index_release. */
+/* Adopt caller-owned device memory as the (single) shard; not freed by nk_index_release.  The rows may still change behind
+ * the library's back (the reference normalises its buffer right after creating it, gpu.go:2100-2106), so no BF16 shadow is
+ * built until the caller says the rows are final: nk_index_refresh_shadow. */
 int nk_index_attach_device_rows(NkIndex *ix, void *rows_dev, uint64_t n_rows);
+/* (Re)build the 16-bit image the fast filter path streams (BF16 shadow + norms of fp32 rows; |x|^2 of fp16 / bf16 rows) from
+ * the rows as they are NOW.  For attached rows this is what gives the documented drop-in route the
+ * headline path; call it again whenever the caller rewrites its buffer. */
+int nk_index_refresh_shadow(NkIndex *ix);
+/* Change the metric of subsequent searches (rows are stored raw and the shadow is metric-independent: nothing is rebuilt). */
+int nk_index_set_metric(NkIndex *ix, int metric);
+/* Score floor of subsequent searches, evaluated INSIDE the kernels (it seeds every query's running threshold, so it also
+ * prunes): cosine / dot — rows scoring below min_score are never returned (VectorIndex.Search minSimilarity,
+ * vector_index.go:339-352; queryNodes keeps a node only if bestScore >= 0, call_vector.go:243); euclidean — the value is a
+ * MAXIMUM distance.  Queries with fewer than k admissible rows return 0xffffffff / 0 in the unused slots.  -INFINITY
+ * (euclidean: +INFINITY or any negative value) clears it. */
+int nk_index_set_min_score(NkIndex *ix, float min_score);
 int nk_index_set_path(NkIndex *ix, int path);
 uint64_t nk_index_rows(const NkIndex *ix);
 int nk_index_stats(const NkIndex *ix, NkStats *out);
@@ -164,6 +188,18 @@ int nk_index_stats(const NkIndex *ix, NkStats *out);
  * queued behind it produced the result, out[2] = bit pattern of max |x|^2 seen by that search, out[3] = 1 if the BF16
  * shadow stage overflowed and the TF32 filter over the fp32 rows re-ran the search. */
 int nk_index_debug_flags(NkIndex *ix, int out[4]);
+/* Cumulative diagnostics of shard 0: out[0] = filter searches whose first (16-bit) stage overflowed its margin buffers and
+ * re-ran through the TF32 filter, out[1] = filter searches that fell through to the exact kernels, out[2] = longest
+ * per-query survivor list of the last filter search.  (Retry rate of a corpus = out[0..1] / searches.) */
+int nk_index_debug_counters(NkIndex *ix, uint64_t out[4]);
+/* Tests only: the raw score estimate and the error bound the filter kernels compare with, for EVERY (row, query) pair of
+ * a single-device index: est_host / bnd_host are [rows x Q] floats (row-major, Q <= 64).  which = NK_PATH_TENSOR_FILTER
+ * (1xTF32 pass over fp32 rows) or NK_PATH_TENSOR_SHADOW (16-bit pass).  The filters are sound iff |est - exact| <= bnd;
+ * tests/test_gpu_error_model.py measures the worst err / bnd ratio against fp64 on adversarial data. */
+int nk_debug_filter_dump(NkIndex *ix, const float *queries_host, uint32_t Q, int which, float *est_host, float *bnd_host);
+/* Device-resident searches return before the device has run: this waits for `stream` (and the index's own streams), reads
+ * and clears the sticky internal-overflow word nk_search checks on every call, and returns 0 / -1 with that message. */
+int nk_index_status(NkIndex *ix, void *stream);
 /* Which kernel the last search used: NK_PATH_SIMT / _TENSOR / _TENSOR_FILTER / _TENSOR_SHADOW (-1: null index). */
 int nk_index_last_path(const NkIndex *ix);
 /* Device-side timing of the dominant kernel (bench.py roofline): when enabled, the main scan launches of
@@ -199,6 +235,38 @@ int nk_search_keys_device(NkIndex *ix, const float *queries_dev, uint32_t Q, uin
  * stream == NULL it synchronises the device first and returns after the merge has completed. */
 int nk_merge_keys_device(int device_id, const uint64_t *keys_dev, uint32_t n_lists, uint32_t Q, uint32_t k,
                          int metric, uint32_t *out_idx_dev, float *out_score_dev, void *stream);
+
+/* Best-of-chunks per node — the scoring loop of db.index.vector.queryNodes (call_vector.go:177-256) on the device.  Rows are
+ * chunk embeddings; group_of_row[r] in [0, n_groups) is the node row r belongs to (host array, one entry per row; NULL
+ * clears; cleared by row-count changing mutations like the row mask).  nk_search_groups scores ONE query against every
+ * admissible row (row mask = label filter, score floor = "bestScore >= 0"), keeps each node's best chunk with a per-node
+ * atomic max (segment-max) and returns the k best nodes: out_group / out_row / out_score [k] = node id, row of its best
+ * chunk, that chunk's score (euclidean: distance), ordered by (score desc, row asc).  Returns the number of nodes found.
+ * Exact fp32 arithmetic, no over-select loop.  Single-device indexes. */
+int nk_index_set_row_groups(NkIndex *ix, const uint32_t *group_of_row, uint64_t n_rows, uint32_t n_groups);
+int nk_search_groups(NkIndex *ix, const float *query_host, uint32_t k, uint32_t *out_group, uint32_t *out_row, float *out_score);
+
+/* Row-sharded search, one rank per GPU, exchange BEHIND the ABI (the reference has a single DeviceID,
+ * gpu.go:218).  Each rank owns rows [row_base, row_base + n) (nk_index_set_row_base).  The only data that crosses GPUs is
+ * every rank's Q*k candidate keys, pushed with plain peer stores over NVLink into a small buffer each rank exports through
+ * CUDA IPC — no NCCL, no host hop, two launches (csrc/exchange.cu):
+ *   c = nk_comm_create(device, rank, world, slot_bytes >= max Q*k*8);  nk_comm_export(c, handle[64]);
+ *   (the host exchanges the world handles by any transport);  nk_comm_connect(c, all_handles = world x 64 B in rank order);
+ *   nk_search_sharded_device(ix, c, queries_dev, Q, k, out_idx_dev, out_score_dev, stream)  on every rank, same sequence.
+ * Ranks living in ONE process (several single-device indexes) use nk_comm_connect_local instead of export / connect.
+ * nk_comm_status synchronises the stream and reports a peer that never arrived (the device-side wait is bounded: 2 s). */
+NkComm *nk_comm_create(int device_id, int rank, int world, size_t slot_bytes);
+int nk_comm_export(NkComm *c, void *handle_out);
+int nk_comm_connect(NkComm *c, const void *handles);
+int nk_comm_connect_local(NkComm **comms, int world);
+int nk_comm_status(NkComm *c, void *stream);
+void nk_comm_release(NkComm *c);
+/* The exchange step alone: keys_dev = this rank's [Q x k] keys (e.g. from nk_search_keys_device, ordered before on
+ * `stream`); writes the merged, decoded result. */
+int nk_comm_exchange_merge(NkComm *c, const uint64_t *keys_dev, uint32_t Q, uint32_t k, int metric, uint32_t *out_idx_dev,
+                           float *out_score_dev, void *stream);
+int nk_search_sharded_device(NkIndex *ix, NkComm *comm, const float *queries_dev, uint32_t Q, uint32_t k, uint32_t *out_idx_dev,
+                             float *out_score_dev, void *stream);
 
 /* Score an explicit subset of rows (global indices) against one query and return them sorted
  * (EmbeddingIndex.ScoreSubset gpu.go:1552-1616, ClusterIndex.SearchCandidates kmeans.go:839-895).

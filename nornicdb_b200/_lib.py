@@ -82,6 +82,23 @@ SIGNATURES = {
     "nk_index_assign_nearest": (_i, [_vp, _vp, C.c_uint32, _i, _vp, _vp]),
     "nk_index_cluster_means": (_i, [_vp, _vp, C.c_uint32, _vp, _vp]),
     "nk_fill_uniform_device": (_i, [_i, _vp, _u64, C.c_uint32, _u64, _u64, _vp]),
+    "nk_index_fill_clustered": (_i, [_vp, _u64, _u64, C.c_uint32, C.c_float, _i]),
+    "nk_index_refresh_shadow": (_i, [_vp]),
+    "nk_index_set_metric": (_i, [_vp, _i]),
+    "nk_index_set_min_score": (_i, [_vp, C.c_float]),
+    "nk_index_debug_counters": (_i, [_vp, C.POINTER(C.c_uint64)]),
+    "nk_debug_filter_dump": (_i, [_vp, _vp, C.c_uint32, _i, _vp, _vp]),
+    "nk_index_status": (_i, [_vp, _vp]),
+    "nk_index_set_row_groups": (_i, [_vp, _vp, _u64, C.c_uint32]),
+    "nk_search_groups": (_i, [_vp, _vp, C.c_uint32, _vp, _vp, _vp]),
+    "nk_comm_create": (_vp, [_i, _i, _i, _sz]),
+    "nk_comm_export": (_i, [_vp, _vp]),
+    "nk_comm_connect": (_i, [_vp, _vp]),
+    "nk_comm_connect_local": (_i, [C.POINTER(_vp), _i]),
+    "nk_comm_status": (_i, [_vp, _vp]),
+    "nk_comm_release": (None, [_vp]),
+    "nk_comm_exchange_merge": (_i, [_vp, _vp, C.c_uint32, C.c_uint32, _i, _vp, _vp, _vp]),
+    "nk_search_sharded_device": (_i, [_vp, _vp, _vp, C.c_uint32, C.c_uint32, _vp, _vp, _vp]),
 }
 
 _lib = None

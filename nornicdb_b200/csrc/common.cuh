@@ -1,11 +1,18 @@
 // common.cuh — shared device/host utilities of libnornic_knn (sm_100a only).
 #pragma once
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges show up under nsys / ncu --nvtx, no-ops otherwise
+
 #include "../../include/nornic_knn.h"
+
+#define NK_RANGE_PUSH(name) nvtxRangePushA(name)
+#define NK_RANGE_POP() nvtxRangePop()
 
 namespace nk {
 
@@ -190,10 +197,12 @@ __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
 //   floor_tau (margin mode): a threshold learnt elsewhere (the cross-CTA shared bound); survivors must also reach it.
 //   gcount != nullptr: `out` is a shared per-query list; the survivors are appended at atomicAdd(gcount, keep)
 //   (entries past out_len are dropped - the caller sizes the list so that cannot happen).
+//   nonfinite (margin mode, nullable): set when the k-th bound or the margin is not finite (k or more NaN / Inf rows, or an
+//   Inf norm): no threshold can be derived from it — everything is kept and the caller escalates to the exact stage.
 template <int PER_LANE>
 __device__ __forceinline__ void warp_prune(uint64_t *cand, int *cnt, float *tau, uint32_t k, int lane, uint64_t *out,
                                            int out_len, bool margin_mode, float margin2, int max_keep,
-                                           float floor_tau = -INFINITY, int *gcount = nullptr) {
+                                           float floor_tau = -INFINITY, int *gcount = nullptr, int *nonfinite = nullptr) {
     int n = *cnt;
     if (n > 32 * PER_LANE) n = 32 * PER_LANE;
     uint64_t v[PER_LANE];
@@ -220,14 +229,19 @@ __device__ __forceinline__ void warp_prune(uint64_t *cand, int *cnt, float *tau,
             // fewer than k LIVE keys (empty slots are key 0): keep them all, no threshold yet
         } else if (margin_mode) {
             new_tau = ord_to_float((uint32_t)(prefix >> 32)) - margin2;
-            thr_key = (uint64_t)ord_bits(new_tau) << 32;  // lowest key with that score
-            if (thr_key == 0ull) thr_key = 1ull;
+            if (!(new_tau < INFINITY)) {  // +inf or NaN: k rows with undecidable bounds, or a non-finite margin
+                new_tau = -INFINITY;
+                if (nonfinite && lane == 0) atomicOr(nonfinite, 8);
+            } else {
+                thr_key = (uint64_t)ord_bits(new_tau) << 32;  // lowest key with that score
+                if (thr_key == 0ull) thr_key = 1ull;
+            }
         } else {
             new_tau = key_score(prefix);
             thr_key = prefix;
         }
     }
-    if (margin_mode && floor_tau > new_tau) {
+    if (floor_tau > new_tau) {  // a threshold learnt elsewhere (shared bound, caller's score floor) outranks the local one
         new_tau = floor_tau;
         thr_key = (uint64_t)ord_bits(new_tau) << 32;
         if (thr_key == 0ull) thr_key = 1ull;
@@ -268,6 +282,29 @@ __device__ __forceinline__ void warp_prune(uint64_t *cand, int *cnt, float *tau,
         *tau = new_tau;
     }
     __syncwarp();
+}
+// Emission without a selection (filter scans): the buffer holds n <= max_keep live-or-stale keys; append those that still
+// reach thr_key to the query's shared list (the finish kernel does the global selection anyway).  One ballot compaction
+// per 32 entries instead of warp_prune's 32-step radix search: the tail of a scan launch is 64-128 of these per CTA.
+__device__ __forceinline__ void warp_emit_above(const uint64_t *cand, int n, uint64_t thr_key, int lane, uint64_t *out, int out_len,
+                                                int *gcount) {
+    int total = 0;
+    for (int base = 0; base < n; base += 32) {
+        const uint64_t v = base + lane < n ? cand[base + lane] : 0ull;
+        total += __popc(__ballot_sync(0xffffffffu, v >= thr_key));
+    }
+    if (total == 0) return;
+    int goff = 0;
+    if (lane == 0) goff = atomicAdd(gcount, total);
+    goff = __shfl_sync(0xffffffffu, goff, 0);
+    for (int base = 0; base < n; base += 32) {
+        const uint64_t v = base + lane < n ? cand[base + lane] : 0ull;
+        const bool keep = v >= thr_key;
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        const int pos = goff + __popc(m & ((1u << lane) - 1u));
+        if (keep && pos < out_len) out[pos] = v;
+        goff += __popc(m);
+    }
 }
 #endif  // __CUDACC__
 

@@ -7,6 +7,7 @@
 // fused scan per shard + a candidate merge; nothing is allocated per query and only Q*k results leave
 // the device.
 #include <algorithm>
+#include <map>
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
@@ -14,11 +15,14 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "scan_tensor_shared.cuh"
 
 namespace nk {
 int scan_tensor(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *out_keys, uint64_t *launches);
 bool scan_tensor_supported(const DeviceInfo &di, const ScanArgs &a);
 int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *out_keys, uint64_t *launches);
+int scan_tensor_filter_tail(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *out_keys, uint64_t *launches);
+int scan_filter_dump(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, int which, float *est, float *bnd, uint32_t ld, uint64_t *launches);
 bool scan_tensor_filter_supported(const DeviceInfo &di, const ScanArgs &a);
 bool shadow_pass_supported(const DeviceInfo &di, const ScanArgs &a);
 bool assign_tensor_supported(const DeviceInfo &di, uint32_t dim, uint32_t K, int metric);
@@ -37,9 +41,18 @@ struct NkShard {
     bool owns = true;
     uint64_t n = 0, cap = 0, base = 0;
     // BF16 shadow of an owned fp32 shard (scan_tensor_shadow.cu): rows [0, shadow_n) are converted; capacity in rows
+    // 16-bit shards (fp16 / bf16) are scanned in place by the same kernel: they only carry xnorm2 (shadow stays null).
     void *shadow = nullptr;
     float *xnorm2 = nullptr, *dnorm2 = nullptr;
     uint64_t shadow_cap = 0, shadow_n = 0;
+    bool shadow_attached = false;  // caller-owned rows: shadow built on request (nk_index_refresh_shadow)
+    // last filter search (host-synchronous API): what the deferred retry tail needs
+    nk::ScanArgs last_args;
+    uint64_t *last_out_keys = nullptr;
+    bool last_filter = false;
+    uint32_t *group = nullptr;  // node id per row (nk_index_set_row_groups), local rows
+    size_t group_bytes = 0;
+    bool group_on = false;
     nk::Workspace ws;
     uint64_t *h_keys = nullptr;  // pinned staging for multi-shard host merge
     size_t h_keys_bytes = 0;
@@ -67,9 +80,16 @@ struct NkIndex {
     std::vector<NkShard> shards;
     uint64_t mask_alive = 0;  // rows that pass the row mask (all shards); meaningful while a mask is set
     bool mask_on = false;
+    float min_score = -INFINITY;  // score floor of subsequent searches, in the API's score domain (nk_index_set_min_score)
+    uint32_t n_groups = 0;        // nk_index_set_row_groups
     NkStats stats{};
     std::mutex mu;
-    size_t esz() const { return dtype == NK_DTYPE_F16 ? 2 : 4; }
+    size_t esz() const { return dtype == NK_DTYPE_F32 ? 4 : 2; }
+    // the floor in key space: euclidean keys are -distance^2 and the API's floor is a maximum distance
+    float key_floor() const {
+        if (metric == NK_METRIC_EUCLIDEAN) return (min_score >= 0.0f && min_score < INFINITY) ? -(min_score * min_score) : -INFINITY;
+        return min_score > -INFINITY ? min_score : -INFINITY;
+    }
     uint32_t dimpad() const { return (dim + 63) / 64 * 64; }
     uint64_t rows() const {
         uint64_t t = 0;
@@ -81,7 +101,8 @@ struct NkIndex {
 // Row-count changing mutations invalidate the row mask (its bits are positions).
 static void drop_row_mask(NkIndex *ix) {
     ix->mask_on = false;
-    for (auto &s : ix->shards) s.mask_on = false;
+    ix->n_groups = 0;
+    for (auto &s : ix->shards) { s.mask_on = false; s.group_on = false; }
 }
 
 static void shard_drop_shadow(NkShard &s) {
@@ -92,10 +113,12 @@ static void shard_drop_shadow(NkShard &s) {
     s.shadow_cap = s.shadow_n = 0;
 }
 
-// Bring the shadow of an owned fp32 shard up to date with rows [0, s.n) (converting only what is missing).  The shadow is
-// an optimisation: if its memory cannot be had the shard simply goes without (the TF32 filter scans the fp32 rows).
+// Bring the 16-bit image of a shard up to date with rows [0, s.n) (converting only what is missing): the BF16 shadow + norms
+// of an fp32 shard, or just the |x|^2 array of an fp16 / bf16 shard (scanned in place).  It is an optimisation: if its memory
+// cannot be had the shard simply goes without (TF32 filter / CUDA-core scan over the rows).
 static int shard_sync_shadow(NkIndex *ix, NkShard &s) {
-    const bool wanted = ix->shadow_on && ix->dtype == NK_DTYPE_F32 && s.owns && ix->dim % 4 == 0 && ix->dim >= 32 && s.n > 0;
+    const bool f32 = ix->dtype == NK_DTYPE_F32;
+    const bool wanted = ix->shadow_on && (s.owns || s.shadow_attached) && ix->dim >= 32 && s.n > 0 && (f32 ? ix->dim % 4 == 0 : ix->dim % 8 == 0);
     if (!wanted) {
         s.shadow_n = 0;
         return 0;
@@ -105,9 +128,9 @@ static int shard_sync_shadow(NkIndex *ix, NkShard &s) {
         NK_CUDA_OK(cudaStreamSynchronize(s.stream));
         shard_drop_shadow(s);
         const uint64_t cap = s.cap > s.n ? s.cap : s.n;
-        cudaError_t e = cudaMalloc(&s.shadow, cap * dimpad * 2);
+        cudaError_t e = f32 ? cudaMalloc(&s.shadow, cap * dimpad * 2) : cudaSuccess;
         if (e == cudaSuccess) e = cudaMalloc((void **)&s.xnorm2, cap * 4);
-        if (e == cudaSuccess) e = cudaMalloc((void **)&s.dnorm2, cap * 4);
+        if (e == cudaSuccess && f32) e = cudaMalloc((void **)&s.dnorm2, cap * 4);
         if (e != cudaSuccess) {
             cudaGetLastError();
             shard_drop_shadow(s);
@@ -116,17 +139,22 @@ static int shard_sync_shadow(NkIndex *ix, NkShard &s) {
         s.shadow_cap = cap;
     }
     if (s.shadow_n < s.n) {
-        if (nk::build_shadow(static_cast<const float *>(s.rows), s.shadow_n, s.n - s.shadow_n, ix->dim, dimpad, s.shadow, s.xnorm2,
-                             s.dnorm2, s.stream))
+        if (f32) {
+            if (nk::build_shadow(static_cast<const float *>(s.rows), s.shadow_n, s.n - s.shadow_n, ix->dim, dimpad, s.shadow, s.xnorm2,
+                                 s.dnorm2, s.stream))
+                return -1;
+        } else if (nk::row_sqnorms16(s.rows, ix->dtype, s.shadow_n, s.n - s.shadow_n, ix->dim, s.xnorm2, s.stream)) {
             return -1;
+        }
         ix->stats.kernel_launches++;
     }
     s.shadow_n = s.n;
     return 0;
 }
 static int shard_shadow_row(NkIndex *ix, NkShard &s, uint64_t local) {  // one row changed in place
-    if (!s.shadow || local >= s.shadow_n) return 0;
+    if (!s.xnorm2 || local >= s.shadow_n) return 0;
     ix->stats.kernel_launches++;
+    if (ix->dtype != NK_DTYPE_F32) return nk::row_sqnorms16(s.rows, ix->dtype, local, 1, ix->dim, s.xnorm2, s.stream);
     return nk::build_shadow(static_cast<const float *>(s.rows), local, 1, ix->dim, ix->dimpad(), s.shadow, s.xnorm2, s.dnorm2, s.stream);
 }
 
@@ -154,7 +182,7 @@ static void parallel_memcpy(void *dst, const void *src, size_t bytes) {
     for (auto &t : th) t.join();
 }
 
-static int stream_h2d(NkShard &s, void *dst_dev, const void *src_host, size_t bytes, bool cvt_f32_to_f16 = false) {
+static int stream_h2d(NkShard &s, void *dst_dev, const void *src_host, size_t bytes, bool cvt_f32_to_f16 = false, int cvt_dtype = NK_DTYPE_F16) {
     if (bytes == 0) return 0;
     for (int i = 0; i < 2; ++i) {
         if (!s.stage[i]) NK_CUDA_OK(cudaHostAlloc(&s.stage[i], STAGE_BYTES, cudaHostAllocDefault));
@@ -170,7 +198,7 @@ static int stream_h2d(NkShard &s, void *dst_dev, const void *src_host, size_t by
         if (cvt_f32_to_f16) {
             float *scratch = reinterpret_cast<float *>(static_cast<char *>(s.cvt) + (size_t)b * STAGE_BYTES);
             NK_CUDA_OK(cudaMemcpyAsync(scratch, s.stage[b], chunk, cudaMemcpyHostToDevice, s.stream));
-            if (nk::convert_f32_to_f16(scratch, static_cast<char *>(dst_dev) + done / 2, chunk / 4, s.stream)) return -1;
+            if (nk::convert_f32_to_16(scratch, static_cast<char *>(dst_dev) + done / 2, cvt_dtype, chunk / 4, s.stream)) return -1;
         } else {
             NK_CUDA_OK(cudaMemcpyAsync(static_cast<char *>(dst_dev) + done, s.stage[b], chunk, cudaMemcpyHostToDevice, s.stream));
         }
@@ -220,8 +248,13 @@ static NkShard *find_shard(NkIndex *ix, uint64_t row, uint64_t *local) {
     return nullptr;
 }
 
+struct ScanOut {  // optional extras of run_scan
+    uint32_t *out_idx = nullptr;   // fused decode (single-shard searches)
+    float *out_score = nullptr;
+    bool defer_tail = false;       // host-synchronous caller: retry stages are queued only if a flag was raised
+};
 static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uint32_t k, uint64_t *out_keys,
-                    cudaStream_t stream);
+                    cudaStream_t stream, const ScanOut &xo = ScanOut());
 
 // k > NK_MAX_K (the reference accepts any k, cuda_bridge.go:327-375): ceil(k / NK_MAX_K) fused CUDA-core passes; pass p+1
 // only admits keys strictly below the last key pass p returned, so the passes tile the ranking exactly.
@@ -237,6 +270,7 @@ static int run_scan_bigk(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q
         a.row_base = custom_rows ? 0 : s.base;
         a.queries = q_dev; a.Q = Q; a.k = kp; a.metric = ix->metric; a.stream = stream; a.below = s.ws.below;
         a.row_mask = (!custom_rows && s.mask_on) ? s.mask : nullptr;
+        a.min_score = custom_rows ? -INFINITY : ix->key_floor();
         if (nk::scan_simt(s.di, a, s.ws, s.ws.keys2, &ix->stats.kernel_launches)) return -1;
         NK_CUDA_OK(cudaMemcpy2DAsync(out_keys + done, (size_t)k * 8, s.ws.keys2, (size_t)kp * 8, (size_t)kp * 8, Q,
                                      cudaMemcpyDeviceToDevice, stream));
@@ -250,35 +284,51 @@ static int run_scan_bigk(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q
 }
 
 static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uint32_t k, uint64_t *out_keys,
-                    cudaStream_t stream) {
-    if (k > NK_MAX_K) return run_scan_bigk(ix, s, q_dev, Q, k, out_keys, stream);
+                    cudaStream_t stream, const ScanOut &xo) {
+    s.last_filter = false;
+    if (k > NK_MAX_K) {
+        if (run_scan_bigk(ix, s, q_dev, Q, k, out_keys, stream)) return -1;
+        if (xo.out_idx) {
+            if (nk::decode_keys(out_keys, Q, k, ix->metric, xo.out_idx, xo.out_score, stream)) return -1;
+            ix->stats.kernel_launches++;
+        }
+        return 0;
+    }
     nk::ScanArgs a;
     a.rows = s.rows; a.dtype = ix->dtype; a.n = (uint32_t)s.n; a.dim = ix->dim; a.row_base = s.base;
     a.queries = q_dev; a.Q = Q; a.k = k; a.metric = ix->metric; a.stream = stream;
     a.row_mask = s.mask_on ? s.mask : nullptr;
+    a.out_idx = xo.out_idx; a.out_score = xo.out_score; a.min_score = ix->key_floor(); a.defer_tail = xo.defer_tail;
     // AUTO (measured on B200, N=10M d=1024, ms per batch).  fp32 rows: CUDA-core scan 5.9 / 6.2 / 6.1 / 7.6 at Q = 1 / 2 /
     // 4 / 8, TF32 tensor filter 5.8 for any Q <= 64 -> CUDA cores keep Q <= 4, tensor cores from 5 queries on.  With a
     // BF16 shadow the filter streams half the bytes: 2.9-3.1 ms for any Q <= 128, so it serves every batch size once the
     // shard is large enough for bytes (not launches) to matter; small shards keep the single-kernel CUDA-core scan at
-    // Q <= 4 (N=100k d=128: 86 us vs 89 us).
-    const bool tensor_ok = nk::scan_tensor_supported(s.di, a), filter_ok = nk::scan_tensor_filter_supported(s.di, a);
-    nk::ScanArgs as = a;  // with the BF16 shadow attached (if the shard has an up-to-date one)
-    if (s.shadow && s.shadow_n == s.n) {
-        as.shadow = s.shadow; as.shadow_dimpad = ix->dimpad(); as.xnorm2 = s.xnorm2; as.dnorm2 = s.dnorm2;
+    // Q <= 4 (N=100k d=128: 86 us vs 89 us).  16-bit shards: the 16-bit tensor pass from 5 queries on (the CUDA-core scan
+    // already streams the minimum bytes at Q <= 4).
+    nk::ScanArgs as = a;  // with the 16-bit image attached (if the shard has an up-to-date one)
+    if (s.xnorm2 && s.shadow_n == s.n) {
+        if (ix->dtype == NK_DTYPE_F32) {
+            as.shadow = s.shadow; as.dnorm2 = s.dnorm2;
+        } else {
+            as.shadow = s.rows; as.shadow_native = true;
+        }
+        as.shadow_dimpad = ix->dimpad(); as.xnorm2 = s.xnorm2;
     }
-    const bool shadow_ok = filter_ok && nk::shadow_pass_supported(s.di, as);
+    const bool tensor_ok = nk::scan_tensor_supported(s.di, a);
+    const bool filter_ok = ix->dtype == NK_DTYPE_F32 && nk::scan_tensor_filter_supported(s.di, a);
+    const bool shadow_ok = as.shadow != nullptr && nk::shadow_pass_supported(s.di, as) && nk::scan_tensor_filter_supported(s.di, as);
     int use = NK_PATH_SIMT;
     if (ix->path == NK_PATH_TENSOR || ix->path == NK_PATH_TENSOR_FILTER || ix->path == NK_PATH_TENSOR_SHADOW) {
         if (!(ix->path == NK_PATH_TENSOR ? tensor_ok : ix->path == NK_PATH_TENSOR_FILTER ? filter_ok : shadow_ok)) {
             nk::set_error("tensor path %d does not support this shape (dim=%u dtype=%d metric=%d Q=%u k=%u shadow=%d)", ix->path, ix->dim,
-                          ix->dtype, ix->metric, Q, k, (int)(s.shadow != nullptr));
+                          ix->dtype, ix->metric, Q, k, (int)(as.shadow != nullptr));
             return -1;
         }
         use = ix->path;
     } else if (ix->path == NK_PATH_AUTO) {
         const bool big_shard = (uint64_t)s.n * ix->dim * 4 >= (64ull << 20);
         if (Q >= 5) use = shadow_ok ? NK_PATH_TENSOR_SHADOW : filter_ok ? NK_PATH_TENSOR_FILTER : tensor_ok ? NK_PATH_TENSOR : NK_PATH_SIMT;
-        else if (shadow_ok && big_shard) use = NK_PATH_TENSOR_SHADOW;
+        else if (shadow_ok && big_shard && ix->dtype == NK_DTYPE_F32) use = NK_PATH_TENSOR_SHADOW;
     }
     if (use == NK_PATH_TENSOR_SHADOW) a = as;
     const bool use_tensor = use != NK_PATH_SIMT;
@@ -289,9 +339,13 @@ static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uin
         NK_CUDA_OK(cudaEventCreate(&e1));
         a.ev_begin = e0; a.ev_end = e1; a.main_launches = &main_launches;
     }
-    int rc = (use == NK_PATH_TENSOR_FILTER || use == NK_PATH_TENSOR_SHADOW) ? nk::scan_tensor_filter(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches)
-             : use == NK_PATH_TENSOR      ? nk::scan_tensor(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches)
-                                          : nk::scan_simt(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches);
+    const bool is_filter = use == NK_PATH_TENSOR_FILTER || use == NK_PATH_TENSOR_SHADOW;
+    NK_RANGE_PUSH(use == NK_PATH_TENSOR_SHADOW ? "nk:scan:shadow" : use == NK_PATH_TENSOR_FILTER ? "nk:scan:tf32-filter"
+                  : use == NK_PATH_TENSOR ? "nk:scan:3xtf32" : "nk:scan:simt");
+    int rc = is_filter ? nk::scan_tensor_filter(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches)
+             : use == NK_PATH_TENSOR ? nk::scan_tensor(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches)
+                                     : nk::scan_simt(s.di, a, s.ws, out_keys, &ix->stats.kernel_launches);
+    NK_RANGE_POP();
     if (ix->timing_on) {
         if (rc == 0 && main_launches) {
             s.timing.emplace_back(e0, e1);
@@ -302,10 +356,43 @@ static int run_scan(NkIndex *ix, NkShard &s, const float *q_dev, uint32_t Q, uin
         }
     }
     ix->last_path = use;
+    if (rc == 0 && is_filter) {
+        s.last_filter = true;
+        s.last_args = a;
+        s.last_args.ev_begin = s.last_args.ev_end = nullptr;
+        s.last_args.main_launches = nullptr;
+        s.last_out_keys = out_keys;
+    }
     if (rc == 0)
-        ix->stats.bytes_scanned += use == NK_PATH_TENSOR_SHADOW ? (uint64_t)s.n * ix->dimpad() * 2 * ((Q + 127) / 128)
+        ix->stats.bytes_scanned += use == NK_PATH_TENSOR_SHADOW ? (uint64_t)s.n * (ix->dtype == NK_DTYPE_F32 ? ix->dimpad() : ix->dim) * 2 * ((Q + 127) / 128)
                                    : (uint64_t)s.n * ix->dim * ix->esz() * (use == NK_PATH_TENSOR_FILTER ? ((Q + 127) / 128) : use_tensor ? ((Q + 63) / 64) : ((Q + 7) / 8));
     return rc;
+}
+
+// Host-synchronous searches defer the retry / exact stages of the filter paths: after the stream has drained, look at the
+// status words; only if a stage overflowed (adversarial near-ties, NaN rows) queue the tail, wait again and let the caller
+// re-read the results.  Returns 1 if a retry ran, 0 if not, -1 on error (a fatal candidate-buffer overflow included).
+static int finish_deferred(NkIndex *ix, NkShard &s) {
+    int h[nk::NK_FLAG_WORDS];
+    NK_CUDA_OK(cudaMemcpyAsync(h, s.ws.flags, sizeof(h), cudaMemcpyDeviceToHost, s.stream));
+    NK_CUDA_OK(cudaStreamSynchronize(s.stream));
+    int retried = 0;
+    if (s.last_filter && s.last_args.defer_tail && (h[nk::FLAG_RETRY] || h[nk::FLAG_OVERFLOW])) {
+        NK_RANGE_PUSH("nk:retry-tail");
+        const int rc = nk::scan_tensor_filter_tail(s.di, s.last_args, s.ws, s.last_out_keys, &ix->stats.kernel_launches);
+        NK_RANGE_POP();
+        if (rc) return -1;
+        NK_CUDA_OK(cudaMemcpyAsync(h, s.ws.flags, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        NK_CUDA_OK(cudaStreamSynchronize(s.stream));
+        retried = 1;
+    }
+    s.last_filter = false;
+    if (h[nk::FLAG_FATAL]) {
+        cudaMemsetAsync(s.ws.flags, 0, sizeof(int), s.stream);
+        nk::set_error("internal: candidate buffer overflow (flag=%d)", h[nk::FLAG_FATAL]);
+        return -1;
+    }
+    return retried;
 }
 
 extern "C" {
@@ -318,7 +405,7 @@ NkIndex *nk_index_create(const int *device_ids, int n_devices, uint32_t dim, int
         nk::set_error("nk_index_create: need >= 1 device and dim > 0");
         return nullptr;
     }
-    if (dtype != NK_DTYPE_F32 && dtype != NK_DTYPE_F16) {
+    if (dtype != NK_DTYPE_F32 && dtype != NK_DTYPE_F16 && dtype != NK_DTYPE_BF16) {
         nk::set_error("nk_index_create: unknown dtype %d", dtype);
         return nullptr;
     }
@@ -328,7 +415,7 @@ NkIndex *nk_index_create(const int *device_ids, int n_devices, uint32_t dim, int
     }
     NkIndex *ix = new NkIndex();
     ix->dim = dim; ix->dtype = dtype; ix->metric = metric;
-    if (const char *e = getenv("NK_SHADOW")) ix->shadow_on = atoi(e) != 0;
+    if (const char *e = getenv("NK_SHADOW")) ix->shadow_on = atoi(e) != 0;  // read once, at creation
     ix->stats.dim = dim; ix->stats.n_devices = (uint32_t)n_devices;
     ix->shards.resize(n_devices);
     for (int i = 0; i < n_devices; ++i) {
@@ -337,8 +424,8 @@ NkIndex *nk_index_create(const int *device_ids, int n_devices, uint32_t dim, int
         cudaError_t e = cudaSetDevice(s.device);
         if (e == cudaSuccess && nk::query_device_info(s.device, &s.di) != 0) e = cudaErrorUnknown;
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaMalloc((void **)&s.ws.flags, sizeof(int) * 8);
-        if (e == cudaSuccess) e = cudaMemset(s.ws.flags, 0, sizeof(int) * 8);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&s.ws.flags, sizeof(int) * nk::NK_FLAG_WORDS);
+        if (e == cudaSuccess) e = cudaMemset(s.ws.flags, 0, sizeof(int) * nk::NK_FLAG_WORDS);
         if (e != cudaSuccess) {
             if (e != cudaErrorUnknown) nk::set_error("nk_index_create(device %d): %s", s.device, cudaGetErrorString(e));
             cudaGetLastError();
@@ -366,6 +453,7 @@ void nk_index_release(NkIndex *ix) {
         }
         if (s.cvt) cudaFree(s.cvt);
         if (s.mask) cudaFree(s.mask);
+        if (s.group) cudaFree(s.group);
         s.ws.release();
     }
     delete ix;
@@ -376,19 +464,20 @@ static int upload_impl(NkIndex *ix, const void *rows_host, uint64_t n_rows, bool
     if (n_rows && !rows_host) { nk::set_error("null rows"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
     drop_row_mask(ix);
-    const bool cvt = src_is_f32 && ix->dtype == NK_DTYPE_F16;
+    const bool cvt = src_is_f32 && ix->dtype != NK_DTYPE_F32;
     const size_t rb = (size_t)ix->dim * ix->esz(), src_rb = (size_t)ix->dim * (cvt ? 4 : ix->esz());
     const uint64_t G = ix->shards.size();
-    if (n_rows / G + 1 > 0xfffffff0ull) { nk::set_error("shard exceeds 2^32 rows"); return -1; }
+    // global row ids are 32-bit on this boundary (SearchResult.Index uint32, cuda_bridge.go:425-428)
+    if (ix->row_base + n_rows > 0xfffffff0ull) { nk::set_error("index exceeds 2^32 rows (row ids are uint32)"); return -1; }
     uint64_t off = 0;
     for (uint64_t g = 0; g < G; ++g) {
         NkShard &s = ix->shards[g];
         uint64_t cnt = n_rows * (g + 1) / G - n_rows * g / G;  // contiguous range [g*N/G, (g+1)*N/G)
         NK_CUDA_OK(cudaSetDevice(s.device));
-        if (!s.owns) { s.rows = nullptr; s.owns = true; s.cap = 0; }
+        if (!s.owns) { s.rows = nullptr; s.owns = true; s.cap = 0; s.shadow_attached = false; }
         s.n = 0;
         if (shard_reserve_rows(ix, s, cnt, false)) return -1;
-        if (stream_h2d(s, s.rows, static_cast<const char *>(rows_host) + off * src_rb, cnt * src_rb, cvt)) return -1;
+        if (stream_h2d(s, s.rows, static_cast<const char *>(rows_host) + off * src_rb, cnt * src_rb, cvt, ix->dtype)) return -1;
         s.n = cnt;
         s.shadow_n = 0;
         if (shard_sync_shadow(ix, s)) return -1;
@@ -437,7 +526,7 @@ int nk_index_append(NkIndex *ix, const void *rows_host, uint64_t n_rows) {
     drop_row_mask(ix);
     NkShard &s = ix->shards.back();
     const size_t rb = (size_t)ix->dim * ix->esz();
-    if (s.n + n_rows > 0xfffffff0ull) { nk::set_error("shard exceeds 2^32 rows"); return -1; }
+    if (ix->row_base + ix->rows() + n_rows > 0xfffffff0ull) { nk::set_error("index exceeds 2^32 rows (row ids are uint32)"); return -1; }
     NK_CUDA_OK(cudaSetDevice(s.device));
     if (shard_reserve_rows(ix, s, s.n + n_rows, true)) return -1;
     if (stream_h2d(s, (char *)s.rows + s.n * rb, rows_host, n_rows * rb)) return -1;
@@ -480,8 +569,16 @@ int nk_index_remove_swap(NkIndex *ix, uint64_t row) {
     if (row != total - 1) {
         const char *src = (const char *)last->rows + (last->n - 1) * rb;
         char *dst = (char *)s->rows + local * rb;
+        // The copy must be ordered with the shard's own stream (non-blocking streams do not synchronise with the legacy
+        // default stream): drain the source shard first when it is another device, then copy ON s->stream so that the
+        // shadow / norm rebuild queued behind reads the new row.
+        if (last != s) {
+            NK_CUDA_OK(cudaSetDevice(last->device));
+            NK_CUDA_OK(cudaStreamSynchronize(last->stream));
+        }
         NK_CUDA_OK(cudaSetDevice(s->device));
-        NK_CUDA_OK(cudaMemcpy(dst, src, rb, cudaMemcpyDefault));  // same or peer device
+        if (last->device == s->device) NK_CUDA_OK(cudaMemcpyAsync(dst, src, rb, cudaMemcpyDeviceToDevice, s->stream));
+        else NK_CUDA_OK(cudaMemcpyPeerAsync(dst, s->device, src, last->device, rb, s->stream));
         if (shard_shadow_row(ix, *s, local)) return -1;
         NK_CUDA_OK(cudaStreamSynchronize(s->stream));
     }
@@ -491,21 +588,23 @@ int nk_index_remove_swap(NkIndex *ix, uint64_t row) {
     return 0;
 }
 
-int nk_index_fill_uniform(NkIndex *ix, uint64_t n_rows, uint64_t seed) {
+static int fill_impl(NkIndex *ix, uint64_t n_rows, uint64_t seed, uint32_t centres, float sigma, int unit) {
     if (!ix) { nk::set_error("null index"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
     drop_row_mask(ix);
     const uint64_t G = ix->shards.size();
-    if (n_rows / G + 1 > 0xfffffff0ull) { nk::set_error("shard exceeds 2^32 rows"); return -1; }
+    if (ix->row_base + n_rows > 0xfffffff0ull) { nk::set_error("index exceeds 2^32 rows (row ids are uint32)"); return -1; }
     uint64_t off = 0;
     for (uint64_t g = 0; g < G; ++g) {
         NkShard &s = ix->shards[g];
         uint64_t cnt = n_rows * (g + 1) / G - n_rows * g / G;
         NK_CUDA_OK(cudaSetDevice(s.device));
-        if (!s.owns) { s.rows = nullptr; s.owns = true; s.cap = 0; }
+        if (!s.owns) { s.rows = nullptr; s.owns = true; s.cap = 0; s.shadow_attached = false; }
         s.n = 0;
         if (shard_reserve_rows(ix, s, cnt, false)) return -1;
-        if (nk::fill_uniform(s.rows, ix->dtype, cnt, ix->dim, seed, ix->row_base + off, s.stream)) return -1;
+        if (centres ? nk::fill_clustered(s.rows, ix->dtype, cnt, ix->dim, seed, ix->row_base + off, centres, sigma, unit, s.stream)
+                    : nk::fill_uniform(s.rows, ix->dtype, cnt, ix->dim, seed, ix->row_base + off, s.stream))
+            return -1;
         ix->stats.kernel_launches++;
         s.n = cnt;
         s.shadow_n = 0;
@@ -520,6 +619,12 @@ int nk_index_fill_uniform(NkIndex *ix, uint64_t n_rows, uint64_t seed) {
     return 0;
 }
 
+int nk_index_fill_uniform(NkIndex *ix, uint64_t n_rows, uint64_t seed) { return fill_impl(ix, n_rows, seed, 0, 0.0f, 0); }
+int nk_index_fill_clustered(NkIndex *ix, uint64_t n_rows, uint64_t seed, uint32_t n_centres, float sigma, int unit_norm) {
+    if (n_centres == 0) { nk::set_error("nk_index_fill_clustered: n_centres must be >= 1"); return -1; }
+    return fill_impl(ix, n_rows, seed, n_centres, sigma, unit_norm);
+}
+
 int nk_index_set_row_base(NkIndex *ix, uint64_t row_base) {
     if (!ix) { nk::set_error("null index"); return -1; }
     if (ix->shards.size() != 1) { nk::set_error("row_base applies to single-device indexes"); return -1; }
@@ -532,15 +637,50 @@ int nk_index_set_row_base(NkIndex *ix, uint64_t row_base) {
 int nk_index_attach_device_rows(NkIndex *ix, void *rows_dev, uint64_t n_rows) {
     if (!ix) { nk::set_error("null index"); return -1; }
     if (ix->shards.size() != 1) { nk::set_error("attach applies to single-device indexes"); return -1; }
-    if (n_rows > 0xfffffff0ull) { nk::set_error("shard exceeds 2^32 rows"); return -1; }
+    if (ix->row_base + n_rows > 0xfffffff0ull) { nk::set_error("index exceeds 2^32 rows (row ids are uint32)"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
     NkShard &s = ix->shards[0];
     NK_CUDA_OK(cudaSetDevice(s.device));
     if (s.rows && s.owns) NK_CUDA_OK(cudaFree(s.rows));
-    shard_drop_shadow(s);  // caller-owned rows may change behind the library's back: no shadow
+    // caller-owned rows may change behind the library's back (cuda_normalize_vectors runs right after NewBuffer,
+    // gpu.go:2100-2106): no shadow until the caller says the rows are final (nk_index_refresh_shadow)
+    NK_CUDA_OK(cudaStreamSynchronize(s.stream));
+    shard_drop_shadow(s);
     drop_row_mask(ix);
-    s.rows = rows_dev; s.owns = false; s.n = n_rows; s.cap = n_rows;
+    s.rows = rows_dev; s.owns = false; s.n = n_rows; s.cap = n_rows; s.shadow_attached = false;
     rebase(ix);
+    return 0;
+}
+
+// (Re)build the 16-bit image of every shard from the rows as they are now.  For attached (caller-owned) rows this is the
+// explicit "rows are final" signal that gives the documented drop-in route the fast filter path; for library-owned shards
+// it is a no-op unless rows were changed behind the library's back.
+int nk_index_refresh_shadow(NkIndex *ix) {
+    if (!ix) { nk::set_error("null index"); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    for (auto &s : ix->shards) {
+        NK_CUDA_OK(cudaSetDevice(s.device));
+        if (!s.owns) s.shadow_attached = true;
+        s.shadow_n = 0;
+        if (shard_sync_shadow(ix, s)) return -1;
+        NK_CUDA_OK(cudaStreamSynchronize(s.stream));
+    }
+    return 0;
+}
+
+int nk_index_set_metric(NkIndex *ix, int metric) {
+    if (!ix) { nk::set_error("null index"); return -1; }
+    if (metric < NK_METRIC_COSINE || metric > NK_METRIC_EUCLIDEAN) { nk::set_error("unknown metric %d", metric); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->metric = metric;  // rows are stored raw and the shadow's norms are metric-independent: nothing to rebuild
+    return 0;
+}
+
+int nk_index_set_min_score(NkIndex *ix, float min_score) {
+    if (!ix) { nk::set_error("null index"); return -1; }
+    if (min_score != min_score) { nk::set_error("min_score is NaN"); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->min_score = min_score;
     return 0;
 }
 
@@ -599,10 +739,65 @@ int nk_index_debug_flags(NkIndex *ix, int out[4]) {
     NkShard &s = ix->shards[0];
     NK_CUDA_OK(cudaSetDevice(s.device));
     NK_CUDA_OK(cudaDeviceSynchronize());
-    int h[8];
-    NK_CUDA_OK(cudaMemcpy(h, s.ws.flags, 8 * sizeof(int), cudaMemcpyDeviceToHost));
-    out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; out[3] = h[5];
+    int h[nk::NK_FLAG_WORDS];
+    NK_CUDA_OK(cudaMemcpy(h, s.ws.flags, sizeof(h), cudaMemcpyDeviceToHost));
+    out[0] = h[nk::FLAG_FATAL]; out[1] = h[nk::FLAG_OVERFLOW]; out[2] = h[nk::FLAG_MAXXX]; out[3] = h[nk::FLAG_RETRY];
     return 0;
+}
+
+// Cumulative diagnostics of shard 0 since creation: out[0] = filter searches whose first (16-bit) stage overflowed and re-ran
+// through the TF32 filter, out[1] = filter searches that fell through to the exact kernels, out[2] = longest per-query
+// survivor list of the last filter search.  bench.py reports out[0..1] / searches as the retry rate of a corpus.
+int nk_index_debug_counters(NkIndex *ix, uint64_t out[4]) {
+    if (!ix || !out || ix->shards.empty()) { nk::set_error("null argument"); return -1; }
+    NkShard &s = ix->shards[0];
+    NK_CUDA_OK(cudaSetDevice(s.device));
+    NK_CUDA_OK(cudaDeviceSynchronize());
+    int h[nk::NK_FLAG_WORDS];
+    NK_CUDA_OK(cudaMemcpy(h, s.ws.flags, sizeof(h), cudaMemcpyDeviceToHost));
+    out[0] = (uint64_t)h[nk::FLAG_N_RETRY]; out[1] = (uint64_t)h[nk::FLAG_N_EXACT]; out[2] = (uint64_t)h[nk::FLAG_LONGEST]; out[3] = 0;
+    return 0;
+}
+
+// Tests only: the raw score estimate and the error bound the filter kernels work with, for every (row, query) pair of a
+// single-device index (rows x Q floats each, row-major [row][query], host buffers).  which = NK_PATH_TENSOR_FILTER (TF32
+// pass over fp32 rows) or NK_PATH_TENSOR_SHADOW (16-bit pass).  The filters are sound iff |est - exact score| <= bnd.
+int nk_debug_filter_dump(NkIndex *ix, const float *queries_host, uint32_t Q, int which, float *est_host, float *bnd_host) {
+    NkShard *s;
+    if (!ix || ix->shards.size() != 1) { nk::set_error("single-device index required"); return -1; }
+    s = &ix->shards[0];
+    if (!queries_host || !est_host || !bnd_host || Q == 0 || Q > 64 || s->n == 0) { nk::set_error("bad argument (1 <= Q <= 64, non-empty index)"); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    NK_CUDA_OK(cudaSetDevice(s->device));
+    const size_t cells = (size_t)s->n * Q;
+    float *d = nullptr;
+    NK_CUDA_OK(cudaMalloc((void **)&d, cells * 8));
+    int rc = -1;
+    do {
+        if (nk::ws_reserve((void **)&s->ws.queries, &s->ws.queries_bytes, (size_t)Q * ix->dim * 4)) break;
+        if (cudaMemcpyAsync(s->ws.queries, queries_host, (size_t)Q * ix->dim * 4, cudaMemcpyHostToDevice, s->stream) != cudaSuccess) break;
+        if (cudaMemsetAsync(d, 0, cells * 8, s->stream) != cudaSuccess) break;
+        nk::ScanArgs a;
+        a.rows = s->rows; a.dtype = ix->dtype; a.n = (uint32_t)s->n; a.dim = ix->dim; a.row_base = s->base;
+        a.queries = s->ws.queries; a.Q = Q; a.k = 1; a.metric = ix->metric; a.stream = s->stream;
+        if (s->xnorm2 && s->shadow_n == s->n) {
+            if (ix->dtype == NK_DTYPE_F32) { a.shadow = s->shadow; a.dnorm2 = s->dnorm2; }
+            else { a.shadow = s->rows; a.shadow_native = true; }
+            a.shadow_dimpad = ix->dimpad(); a.xnorm2 = s->xnorm2;
+        }
+        if (nk::scan_filter_dump(s->di, a, s->ws, which, d, d + cells, Q, &ix->stats.kernel_launches)) break;
+        if (cudaMemcpyAsync(est_host, d, cells * 4, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) break;
+        if (cudaMemcpyAsync(bnd_host, d + cells, cells * 4, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) break;
+        if (cudaStreamSynchronize(s->stream) != cudaSuccess) break;
+        rc = 0;
+    } while (0);
+    if (rc != 0) {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) nk::set_error("nk_debug_filter_dump: %s", cudaGetErrorString(e));
+        cudaStreamSynchronize(s->stream);
+    }
+    cudaFree(d);
+    return rc;
 }
 
 int nk_index_last_path(const NkIndex *ix) { return ix ? ix->last_path : -1; }
@@ -654,18 +849,6 @@ int nk_index_read_rows(NkIndex *ix, uint64_t row, uint64_t n_rows, void *rows_ho
     return 0;
 }
 
-static int check_flags(NkShard &s) {
-    int h[1] = {0};
-    NK_CUDA_OK(cudaMemcpyAsync(h, s.ws.flags, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
-    NK_CUDA_OK(cudaStreamSynchronize(s.stream));
-    if (h[0]) {
-        cudaMemsetAsync(s.ws.flags, 0, sizeof(int), s.stream);
-        nk::set_error("internal: candidate buffer overflow (flag=%d)", h[0]);
-        return -1;
-    }
-    return 0;
-}
-
 int nk_search(NkIndex *ix, const float *queries_host, uint32_t Q, uint32_t k, uint32_t *out_idx, float *out_score) {
     if (!ix) { nk::set_error("null index"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
@@ -677,34 +860,46 @@ int nk_search(NkIndex *ix, const float *queries_host, uint32_t Q, uint32_t k, ui
     const size_t qbytes = (size_t)Q * ix->dim * sizeof(float);
     ix->stats.searches++;
     ix->stats.queries += Q;
+    NK_RANGE_PUSH("nk_search");
+    struct Pop { ~Pop() { NK_RANGE_POP(); } } pop_on_exit;
 
     std::vector<NkShard *> live;
     for (auto &s : ix->shards)
         if (s.n) live.push_back(&s);
+    const bool single = live.size() == 1;
 
-    // Launch every shard asynchronously, then collect.
+    // Launch every shard asynchronously, then collect.  A single shard writes the decoded (index, score) arrays from
+    // the last kernel of its path (no separate decode launch); the retry stages of the filter paths are deferred.
     for (NkShard *s : live) {
         NK_CUDA_OK(cudaSetDevice(s->device));
         if (nk::ws_reserve((void **)&s->ws.queries, &s->ws.queries_bytes, qbytes)) return -1;
         if (nk::ws_reserve((void **)&s->ws.keys, &s->ws.keys_bytes, (size_t)Q * ke * 8)) return -1;
+        ScanOut xo;
+        xo.defer_tail = true;
+        if (single) {
+            if (nk::ws_reserve((void **)&s->ws.out_idx, &s->ws.out_idx_bytes, (size_t)Q * ke * 4)) return -1;
+            if (nk::ws_reserve((void **)&s->ws.out_score, &s->ws.out_score_bytes, (size_t)Q * ke * 4)) return -1;
+            xo.out_idx = s->ws.out_idx; xo.out_score = s->ws.out_score;
+        }
         NK_CUDA_OK(cudaMemcpyAsync(s->ws.queries, queries_host, qbytes, cudaMemcpyHostToDevice, s->stream));
         ix->stats.bytes_h2d += qbytes;
-        if (run_scan(ix, *s, s->ws.queries, Q, ke, s->ws.keys, s->stream)) return -1;
+        if (run_scan(ix, *s, s->ws.queries, Q, ke, s->ws.keys, s->stream, xo)) return -1;
     }
 
-    if (live.size() == 1) {
+    if (single) {
         NkShard *s = live[0];
         NK_CUDA_OK(cudaSetDevice(s->device));
-        if (nk::ws_reserve((void **)&s->ws.out_idx, &s->ws.out_idx_bytes, (size_t)Q * ke * 4)) return -1;
-        if (nk::ws_reserve((void **)&s->ws.out_score, &s->ws.out_score_bytes, (size_t)Q * ke * 4)) return -1;
-        if (nk::decode_keys(s->ws.keys, Q, ke, ix->metric, s->ws.out_idx, s->ws.out_score, s->stream)) return -1;
-        ix->stats.kernel_launches++;
-        NK_CUDA_OK(cudaMemcpy2DAsync(out_idx, (size_t)k * 4, s->ws.out_idx, (size_t)ke * 4, (size_t)ke * 4, Q,
-                                     cudaMemcpyDeviceToHost, s->stream));
-        NK_CUDA_OK(cudaMemcpy2DAsync(out_score, (size_t)k * 4, s->ws.out_score, (size_t)ke * 4, (size_t)ke * 4, Q,
-                                     cudaMemcpyDeviceToHost, s->stream));
-        ix->stats.bytes_d2h += (uint64_t)Q * ke * 8;
-        if (check_flags(*s)) return -1;
+        for (int pass = 0; pass < 2; ++pass) {
+            NK_CUDA_OK(cudaMemcpy2DAsync(out_idx, (size_t)k * 4, s->ws.out_idx, (size_t)ke * 4, (size_t)ke * 4, Q,
+                                         cudaMemcpyDeviceToHost, s->stream));
+            NK_CUDA_OK(cudaMemcpy2DAsync(out_score, (size_t)k * 4, s->ws.out_score, (size_t)ke * 4, (size_t)ke * 4, Q,
+                                         cudaMemcpyDeviceToHost, s->stream));
+            ix->stats.bytes_d2h += (uint64_t)Q * ke * 8;
+            if (pass == 1) { NK_CUDA_OK(cudaStreamSynchronize(s->stream)); break; }
+            const int r = finish_deferred(ix, *s);  // synchronises; > 0: a retry stage rewrote the results
+            if (r < 0) return -1;
+            if (r == 0) break;
+        }
         return (int)ke;
     }
 
@@ -719,12 +914,16 @@ int nk_search(NkIndex *ix, const float *queries_host, uint32_t Q, uint32_t k, ui
             NK_CUDA_OK(cudaMallocHost((void **)&s->h_keys, kbytes + kbytes / 4));
             s->h_keys_bytes = kbytes + kbytes / 4;
         }
+    }
+    for (NkShard *s : live) {
+        NK_CUDA_OK(cudaSetDevice(s->device));
+        if (finish_deferred(ix, *s) < 0) return -1;  // runs this shard's retry stages if it needs them
         NK_CUDA_OK(cudaMemcpyAsync(s->h_keys, s->ws.keys, kbytes, cudaMemcpyDeviceToHost, s->stream));
         ix->stats.bytes_d2h += kbytes;
     }
     for (NkShard *s : live) {
         NK_CUDA_OK(cudaSetDevice(s->device));
-        if (check_flags(*s)) return -1;
+        NK_CUDA_OK(cudaStreamSynchronize(s->stream));
     }
     std::vector<uint64_t> tmp(live.size() * (size_t)ke);
     for (uint32_t q = 0; q < Q; ++q) {
@@ -782,28 +981,48 @@ int nk_search_device(NkIndex *ix, const float *queries_dev, uint32_t Q, uint32_t
                      float *out_score_dev, void *stream) {
     NkShard *s;
     if (single_shard(ix, &s)) return -1;
-    const uint64_t N = s->n;
-    if (k == 0 || N == 0 || Q == 0) return 0;
+    if (k == 0 || Q == 0) return 0;
     if (!queries_dev || !out_idx_dev || !out_score_dev) { nk::set_error("null argument"); return -1; }
-    if (k > N) { nk::set_error("nk_search_device: k=%u > rows=%llu (clamp on the host side)", k, (unsigned long long)N); return -1; }
     if (k > NK_MAX_K_TOTAL) { nk::set_error("k=%u exceeds NK_MAX_K_TOTAL=%u", k, NK_MAX_K_TOTAL); return -1; }
-    std::lock_guard<std::mutex> lk(ix->mu);
+    std::lock_guard<std::mutex> lk(ix->mu);  // the row count is read under the lock (a concurrent append may change it)
+    const uint64_t N = s->n;
+    if (N == 0) return 0;
+    if (k > N) { nk::set_error("nk_search_device: k=%u > rows=%llu (clamp on the host side)", k, (unsigned long long)N); return -1; }
     NK_CUDA_OK(cudaSetDevice(s->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
     if (nk::ws_reserve((void **)&s->ws.keys, &s->ws.keys_bytes, (size_t)Q * k * 8)) return -1;
     ix->stats.searches++;
     ix->stats.queries += Q;
-    if (run_scan(ix, *s, queries_dev, Q, k, s->ws.keys, st)) return -1;
-    if (nk::decode_keys(s->ws.keys, Q, k, ix->metric, out_idx_dev, out_score_dev, st)) return -1;
-    ix->stats.kernel_launches++;
+    ScanOut xo;
+    xo.out_idx = out_idx_dev; xo.out_score = out_score_dev;  // decoded by the last kernel of the path
+    if (run_scan(ix, *s, queries_dev, Q, k, s->ws.keys, st, xo)) return -1;
     return (int)k;
 }
 
-// grow-only per-device scratch of nk_merge_keys_device (no allocation per merge)
-static std::mutex g_merge_mu;
-static uint64_t *g_merge_scratch[64] = {nullptr};
-static size_t g_merge_scratch_bytes[64] = {0};
+// Device-resident searches cannot report a (never expected) candidate-buffer overflow when they return: this call waits
+// for `stream` (NULL = the index's own streams), reads and clears the sticky status word of every shard, and returns 0 or -1
+// with the message nk_search would have given.  Call it wherever the caller synchronises anyway.
+int nk_index_status(NkIndex *ix, void *stream) {
+    if (!ix) { nk::set_error("null index"); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    int bad = 0;
+    for (auto &s : ix->shards) {
+        NK_CUDA_OK(cudaSetDevice(s.device));
+        if (stream) NK_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+        NK_CUDA_OK(cudaStreamSynchronize(s.stream));
+        int h = 0;
+        NK_CUDA_OK(cudaMemcpy(&h, s.ws.flags, sizeof(int), cudaMemcpyDeviceToHost));
+        if (h) {
+            NK_CUDA_OK(cudaMemset(s.ws.flags, 0, sizeof(int)));
+            bad = h;
+        }
+    }
+    if (bad) { nk::set_error("internal: candidate buffer overflow (flag=%d)", bad); return -1; }
+    return 0;
+}
 
+// (No scratch buffer: the merge kernel writes the decoded arrays itself, so concurrent merges on different streams share
+// nothing.)
 int nk_merge_keys_device(int device_id, const uint64_t *keys_dev, uint32_t n_lists, uint32_t Q, uint32_t k, int metric,
                          uint32_t *out_idx_dev, float *out_score_dev, void *stream) {
     if (k == 0 || Q == 0 || n_lists == 0) return 0;
@@ -814,11 +1033,8 @@ int nk_merge_keys_device(int device_id, const uint64_t *keys_dev, uint32_t n_lis
     // No stream given: behave synchronously (the producers may have run on the indexes' own non-blocking streams,
     // which the legacy default stream does not order against).
     if (!st) NK_CUDA_OK(cudaDeviceSynchronize());
-    std::lock_guard<std::mutex> lk(g_merge_mu);
-    if (nk::ws_reserve((void **)&g_merge_scratch[device_id], &g_merge_scratch_bytes[device_id], (size_t)Q * k * 8)) return -1;
-    uint64_t *merged = g_merge_scratch[device_id];
-    int rc = nk::merge_keys(keys_dev, n_lists, (size_t)Q * k, k, Q, k, merged, st);
-    if (rc == 0) rc = nk::decode_keys(merged, Q, k, metric, out_idx_dev, out_score_dev, st);
+    // one fused launch: merge the lists and write the decoded (index, score) arrays; no intermediate key buffer
+    int rc = nk::merge_keys(keys_dev, n_lists, (size_t)Q * k, k, Q, k, nullptr, st, nullptr, 0, out_idx_dev, out_score_dev, metric);
     if (rc == 0 && !st) NK_CUDA_OK(cudaStreamSynchronize(st));
     return rc;
 }
@@ -839,10 +1055,12 @@ int nk_score_subset(NkIndex *ix, const float *query_host, const uint32_t *rows_h
         }
     NK_CUDA_OK(cudaSetDevice(s->device));
     const size_t rb = (size_t)ix->dim * ix->esz();
-    uint32_t *d_rows = nullptr;
-    void *d_gather = nullptr;
-    NK_CUDA_OK(cudaMallocAsync((void **)&d_rows, (size_t)n_subset * 4, s->stream));
-    NK_CUDA_OK(cudaMallocAsync(&d_gather, (size_t)n_subset * rb, s->stream));
+    // grow-only workspace of the shard: no allocation per call (cuda.Device.Search allocates two buffers per query,
+    // cuda_bridge.go:652-663)
+    if (nk::ws_reserve((void **)&s->ws.sub_rows, &s->ws.sub_rows_bytes, (size_t)n_subset * 4)) return -1;
+    if (nk::ws_reserve(&s->ws.sub_gather, &s->ws.sub_gather_bytes, (size_t)n_subset * rb)) return -1;
+    uint32_t *d_rows = s->ws.sub_rows;
+    void *d_gather = s->ws.sub_gather;
     std::vector<uint32_t> local(rows_host, rows_host + n_subset);
     for (auto &r : local) r -= (uint32_t)ix->row_base;
     int rc = 0;
@@ -860,20 +1078,22 @@ int nk_score_subset(NkIndex *ix, const float *query_host, const uint32_t *rows_h
         a.queries = s->ws.queries; a.Q = 1; a.k = ke; a.metric = ix->metric; a.stream = s->stream;
         if (ke > NK_MAX_K) {  // ScoreSubset ranks every candidate (up to MaxCandidates = 5000, vector_pipeline.go:24-31)
             if (run_scan_bigk(ix, *s, s->ws.queries, 1, ke, s->ws.keys, s->stream, d_gather, n_subset, true)) { rc = -1; break; }
-        } else if (nk::scan_simt(s->di, a, s->ws, s->ws.keys, &ix->stats.kernel_launches)) { rc = -1; break; }
-        if (nk::decode_keys(s->ws.keys, 1, ke, ix->metric, s->ws.out_idx, s->ws.out_score, s->stream)) { rc = -1; break; }
+            if (nk::decode_keys(s->ws.keys, 1, ke, ix->metric, s->ws.out_idx, s->ws.out_score, s->stream)) { rc = -1; break; }
+        } else {
+            a.out_idx = s->ws.out_idx; a.out_score = s->ws.out_score;  // decoded by the merge launch
+            if (nk::scan_simt(s->di, a, s->ws, s->ws.keys, &ix->stats.kernel_launches)) { rc = -1; break; }
+        }
         if (cudaMemcpyAsync(pos.data(), s->ws.out_idx, (size_t)ke * 4, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) { rc = -1; break; }
         if (cudaMemcpyAsync(out_score, s->ws.out_score, (size_t)ke * 4, cudaMemcpyDeviceToHost, s->stream) != cudaSuccess) { rc = -1; break; }
     } while (0);
-    cudaFreeAsync(d_rows, s->stream);
-    cudaFreeAsync(d_gather, s->stream);
     if (rc != 0) {
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) nk::set_error("nk_score_subset: %s", cudaGetErrorString(e));
         cudaStreamSynchronize(s->stream);
         return -1;
     }
-    if (check_flags(*s)) return -1;
+    s->last_filter = false;
+    if (finish_deferred(ix, *s) < 0) return -1;
     // positions within the subset -> global row ids (ties broken by subset position, like the stable
     // order of ScoreSubset's input list)
     for (uint32_t i = 0; i < ke; ++i) out_idx[i] = pos[i] < n_subset ? rows_host[pos[i]] : 0xffffffffu;
@@ -899,19 +1119,20 @@ int nk_index_assign_nearest(NkIndex *ix, const float *centroids_host, uint32_t K
         const bool tensor = s.shadow && s.shadow_n == s.n && nk::assign_tensor_supported(s.di, ix->dim, K, metric);
         NkIndex *cx = tensor ? nullptr : nk_index_create(&s.device, 1, ix->dim, NK_DTYPE_F32, metric);
         if (!tensor && !cx) return -1;
-        uint32_t *d_idx = nullptr;
-        float *d_sc = nullptr, *d_cen = nullptr;
-        int32_t *d_prev = nullptr;
-        unsigned long long *d_changed = nullptr, h_changed = 0;
+        // one grow-only scratch buffer per shard, carved up (no cudaMalloc / cudaFree per call)
+        const size_t n4 = (s.n * 4 + 255) & ~(size_t)255, cen_b = tensor ? (((size_t)K * ix->dim * 4 + 255) & ~(size_t)255) : 0;
+        unsigned long long h_changed = 0;
         int rc = tensor ? 0 : nk_index_upload(cx, centroids_host, K);
+        if (rc == 0 && nk::ws_reserve(&s.ws.scratch, &s.ws.scratch_bytes, 3 * n4 + 256 + cen_b)) rc = -1;
+        unsigned char *base = static_cast<unsigned char *>(s.ws.scratch);
+        uint32_t *d_idx = reinterpret_cast<uint32_t *>(base);
+        float *d_sc = reinterpret_cast<float *>(base + n4);
+        int32_t *d_prev = reinterpret_cast<int32_t *>(base + 2 * n4);
+        unsigned long long *d_changed = reinterpret_cast<unsigned long long *>(base + 3 * n4);
+        float *d_cen = reinterpret_cast<float *>(base + 3 * n4 + 256);
         cudaError_t e = cudaSuccess;
         if (rc == 0) {
-            e = cudaMalloc((void **)&d_idx, s.n * 4);
-            if (e == cudaSuccess) e = cudaMalloc((void **)&d_sc, s.n * 4);
-            if (e == cudaSuccess) e = cudaMalloc((void **)&d_prev, s.n * 4);
-            if (e == cudaSuccess) e = cudaMalloc((void **)&d_changed, 8);
-            if (e == cudaSuccess && tensor) e = cudaMalloc((void **)&d_cen, (size_t)K * ix->dim * 4);
-            if (e == cudaSuccess && tensor) e = cudaMemcpyAsync(d_cen, centroids_host, (size_t)K * ix->dim * 4, cudaMemcpyHostToDevice, s.stream);
+            if (tensor) e = cudaMemcpyAsync(d_cen, centroids_host, (size_t)K * ix->dim * 4, cudaMemcpyHostToDevice, s.stream);
             if (e == cudaSuccess) e = cudaMemsetAsync(d_changed, 0, 8, s.stream);
             if (e == cudaSuccess) e = cudaMemcpyAsync(d_prev, assign_io + off, s.n * 4, cudaMemcpyHostToDevice, s.stream);
             if (e != cudaSuccess) rc = -1;
@@ -934,7 +1155,6 @@ int nk_index_assign_nearest(NkIndex *ix, const float *centroids_host, uint32_t K
         }
         if (e != cudaSuccess) { nk::set_error("nk_index_assign_nearest: %s", cudaGetErrorString(e)); cudaGetLastError(); }
         cudaStreamSynchronize(s.stream);
-        cudaFree(d_idx); cudaFree(d_sc); cudaFree(d_prev); cudaFree(d_changed); cudaFree(d_cen);
         ix->stats.kernel_launches += (cx ? cx->stats.kernel_launches : 0) + 1;
         if (cx) nk_index_release(cx);
         if (rc != 0) return -1;
@@ -959,13 +1179,13 @@ int nk_index_cluster_means(NkIndex *ix, const int32_t *assign_host, uint32_t K, 
     for (auto &s : ix->shards) {
         if (s.n == 0) continue;
         NK_CUDA_OK(cudaSetDevice(s.device));
-        double *d_sums = nullptr;
-        unsigned long long *d_counts = nullptr;
-        int32_t *d_assign = nullptr;
-        cudaError_t e = cudaMalloc((void **)&d_sums, KD * 8);
-        if (e == cudaSuccess) e = cudaMalloc((void **)&d_counts, (size_t)K * 8);
-        if (e == cudaSuccess) e = cudaMalloc((void **)&d_assign, s.n * 4);
-        if (e == cudaSuccess) e = cudaMemsetAsync(d_sums, 0, KD * 8, s.stream);
+        const size_t kd8 = (KD * 8 + 255) & ~(size_t)255, k8 = ((size_t)K * 8 + 255) & ~(size_t)255;
+        if (nk::ws_reserve(&s.ws.scratch, &s.ws.scratch_bytes, kd8 + k8 + s.n * 4)) return -1;  // grow-only, reused across calls
+        unsigned char *base = static_cast<unsigned char *>(s.ws.scratch);
+        double *d_sums = reinterpret_cast<double *>(base);
+        unsigned long long *d_counts = reinterpret_cast<unsigned long long *>(base + kd8);
+        int32_t *d_assign = reinterpret_cast<int32_t *>(base + kd8 + k8);
+        cudaError_t e = cudaMemsetAsync(d_sums, 0, KD * 8, s.stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(d_counts, 0, (size_t)K * 8, s.stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_assign, assign_host + off, s.n * 4, cudaMemcpyHostToDevice, s.stream);
         int rc = e == cudaSuccess ? nk::cluster_sums(static_cast<const float *>(s.rows), s.n, ix->dim, d_assign, K, d_sums, d_counts, s.stream) : -1;
@@ -976,7 +1196,6 @@ int nk_index_cluster_means(NkIndex *ix, const int32_t *assign_host, uint32_t K, 
         }
         if (e != cudaSuccess) { nk::set_error("nk_index_cluster_means: %s", cudaGetErrorString(e)); cudaGetLastError(); rc = -1; }
         cudaStreamSynchronize(s.stream);
-        cudaFree(d_sums); cudaFree(d_counts); cudaFree(d_assign);
         if (rc != 0) return -1;
         ix->stats.kernel_launches++;
         for (size_t i = 0; i < KD; ++i) sums[i] += part[i];
@@ -989,6 +1208,96 @@ int nk_index_cluster_means(NkIndex *ix, const int32_t *assign_host, uint32_t K, 
         if (counts_out) counts_out[c] = (uint32_t)counts[c];
     }
     return 0;
+}
+
+// ---- best-of-chunks per node (db.index.vector.queryNodes, call_vector.go:177-256) -------------------------
+// Rows are chunk embeddings; group_of_row[r] = the node row r belongs to (ids in [0, n_groups)).  Stays set until a
+// row-count changing mutation (like the row mask, whose bits are positions).
+int nk_index_set_row_groups(NkIndex *ix, const uint32_t *group_of_row, uint64_t n_rows, uint32_t n_groups) {
+    if (!ix) { nk::set_error("null index"); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (!group_of_row) {
+        ix->n_groups = 0;
+        for (auto &s : ix->shards) s.group_on = false;
+        return 0;
+    }
+    if (ix->shards.size() != 1) { nk::set_error("row groups apply to single-device indexes"); return -1; }
+    if (n_rows != ix->rows()) { nk::set_error("row groups: %llu entries, index has %llu rows", (unsigned long long)n_rows, (unsigned long long)ix->rows()); return -1; }
+    if (n_groups == 0) { nk::set_error("row groups: n_groups must be >= 1"); return -1; }
+    for (uint64_t r = 0; r < n_rows; ++r)
+        if (group_of_row[r] >= n_groups) { nk::set_error("row groups: group id %u of row %llu out of range", group_of_row[r], (unsigned long long)r); return -1; }
+    NkShard &s = ix->shards[0];
+    NK_CUDA_OK(cudaSetDevice(s.device));
+    if (nk::ws_reserve((void **)&s.group, &s.group_bytes, (size_t)(n_rows ? n_rows : 1) * 4)) return -1;
+    NK_CUDA_OK(cudaMemcpyAsync(s.group, group_of_row, n_rows * 4, cudaMemcpyHostToDevice, s.stream));
+    NK_CUDA_OK(cudaStreamSynchronize(s.stream));
+    s.group_on = true;
+    ix->n_groups = n_groups;
+    return 0;
+}
+
+// One query against the chunk rows; result = the k best NODES, each with the score and row of its best chunk, ordered by
+// (score desc, best-chunk row asc).  Honours the row mask (label filter) and the score floor (nk_index_set_min_score: the
+// reference keeps a node only if bestScore >= 0, call_vector.go:243).  Exact fp32 scores, no over-select loop: one pass
+// with a per-node atomic max (segment-max), one top-k over the node keys.  Returns the number of nodes found (<= k).
+int nk_search_groups(NkIndex *ix, const float *query_host, uint32_t k, uint32_t *out_group, uint32_t *out_row, float *out_score) {
+    NkShard *s;
+    if (single_shard(ix, &s)) return -1;
+    if (k == 0 || s->n == 0) return 0;
+    if (!query_host || !out_group || !out_row || !out_score) { nk::set_error("null argument"); return -1; }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (!s->group_on || ix->n_groups == 0) { nk::set_error("nk_search_groups: no row groups set (nk_index_set_row_groups)"); return -1; }
+    const uint32_t G = ix->n_groups, ke = k < G ? k : G;
+    if (ke > NK_MAX_K) { nk::set_error("nk_search_groups: k=%u exceeds NK_MAX_K=%u", ke, NK_MAX_K); return -1; }
+    NK_CUDA_OK(cudaSetDevice(s->device));
+    NK_RANGE_PUSH("nk_search_groups");
+    struct Pop { ~Pop() { NK_RANGE_POP(); } } pop_on_exit;
+    if (nk::ws_reserve((void **)&s->ws.queries, &s->ws.queries_bytes, (size_t)ix->dim * 4)) return -1;
+    if (nk::ws_reserve(&s->ws.scratch, &s->ws.scratch_bytes, (size_t)G * 8)) return -1;
+    if (nk::ws_reserve((void **)&s->ws.keys, &s->ws.keys_bytes, (size_t)ke * 8)) return -1;
+    if (nk::ws_reserve((void **)&s->ws.out_idx, &s->ws.out_idx_bytes, (size_t)ke * 8)) return -1;
+    if (nk::ws_reserve((void **)&s->ws.out_score, &s->ws.out_score_bytes, (size_t)ke * 4)) return -1;
+    unsigned long long *best = static_cast<unsigned long long *>(s->ws.scratch);
+    NK_CUDA_OK(cudaMemcpyAsync(s->ws.queries, query_host, (size_t)ix->dim * 4, cudaMemcpyHostToDevice, s->stream));
+    NK_CUDA_OK(cudaMemsetAsync(best, 0, (size_t)G * 8, s->stream));
+    if (nk::group_best(s->rows, ix->dtype, s->n, ix->dim, s->base, s->ws.queries, ix->metric, s->group, s->mask_on ? s->mask : nullptr,
+                       ix->key_floor(), best, s->stream))
+        return -1;
+    if (nk::topk_keys(s->di, best, G, ke, s->ws, s->ws.keys, s->stream)) return -1;
+    if (nk::decode_group_keys(s->ws.keys, ke, ix->metric, s->group, s->base, s->ws.out_idx, s->ws.out_idx + ke, s->ws.out_score, s->stream)) return -1;
+    ix->stats.kernel_launches += 4;
+    ix->stats.searches++; ix->stats.queries++;
+    ix->stats.bytes_scanned += (uint64_t)s->n * ix->dim * ix->esz();
+    NK_CUDA_OK(cudaMemcpyAsync(out_group, s->ws.out_idx, (size_t)ke * 4, cudaMemcpyDeviceToHost, s->stream));
+    NK_CUDA_OK(cudaMemcpyAsync(out_row, s->ws.out_idx + ke, (size_t)ke * 4, cudaMemcpyDeviceToHost, s->stream));
+    NK_CUDA_OK(cudaMemcpyAsync(out_score, s->ws.out_score, (size_t)ke * 4, cudaMemcpyDeviceToHost, s->stream));
+    s->last_filter = false;
+    if (finish_deferred(ix, *s) < 0) return -1;
+    uint32_t found = 0;
+    while (found < ke && out_group[found] != 0xffffffffu) ++found;
+    return (int)found;
+}
+
+// ---- row-sharded search with the exchange behind the ABI (exchange.cu) ----------------------------------------------------
+// One rank per GPU (one process each, or several single-device indexes in one process): scan this rank's shard, push the
+// Q*k candidate keys into every peer's buffer over NVLink, merge what the peers pushed.  Asynchronous on `stream`; every
+// rank must make the same sequence of calls.  out_*_dev: [Q x k] on this rank's device, identical on every rank.
+int nk_search_sharded_device(NkIndex *ix, NkComm *comm, const float *queries_dev, uint32_t Q, uint32_t k, uint32_t *out_idx_dev,
+                             float *out_score_dev, void *stream) {
+    NkShard *s;
+    if (single_shard(ix, &s)) return -1;
+    if (!comm) { nk::set_error("null communicator"); return -1; }
+    if (k == 0 || Q == 0) return 0;
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    {
+        std::lock_guard<std::mutex> lk(ix->mu);
+        NK_CUDA_OK(cudaSetDevice(s->device));
+        if (nk::ws_reserve((void **)&s->ws.keys, &s->ws.keys_bytes, (size_t)Q * k * 8)) return -1;
+    }
+    if (nk_search_keys_device(ix, queries_dev, Q, k, s->ws.keys, st) < 0) return -1;
+    if (nk_comm_exchange_merge(comm, s->ws.keys, Q, k, ix->metric, out_idx_dev, out_score_dev, st) < 0) return -1;
+    ix->stats.kernel_launches += 2;
+    return (int)k;
 }
 
 int nk_fill_uniform_device(int device_id, float *out_dev, uint64_t n_rows, uint32_t dim, uint64_t seed,

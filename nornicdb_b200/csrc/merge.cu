@@ -20,6 +20,13 @@ struct MergeParams {
     uint64_t *out;  // [Q][k]
     const int *only_if;
     uint32_t list_len;  // entries per input list (may differ from the output k)
+    uint32_t *dec_idx;  // optional fused decode
+    float *dec_score;
+    int dec_metric;
+    // optional: the lists are being written by PEER GPUs (exchange.cu); list l is complete once wait_flags[l] >= wait_epoch
+    const uint32_t *wait_flags;
+    uint32_t wait_epoch;
+    int *wait_err;  // set to 2 if a peer did not arrive within ~2 s (never spin forever: a hung GPU is a strike)
 };
 
 // One CTA per query.  Streams the n_lists*k candidate keys through a 2048-wide sort buffer, keeping
@@ -32,6 +39,25 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(MergeParams p
     const uint64_t *base = p.keys + (size_t)q * p.q_stride;
     const uint64_t total = (uint64_t)p.n_lists * p.list_len;
     const int tid = threadIdx.x;
+    if (p.wait_flags) {
+        // fused exchange wait: thread l polls peer l's arrival word (system-scope acquire), bounded by a wall-clock timeout
+        if (tid < (int)p.n_lists) {
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            for (;;) {
+                uint32_t v;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.wait_flags + tid) : "memory");
+                if ((int32_t)(v - p.wait_epoch) >= 0) break;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > 2000000000ull) {
+                    atomicExch(p.wait_err, 2);
+                    break;
+                }
+                __nanosleep(64);
+            }
+        }
+        __syncthreads();
+    }
 
     // sort width: the whole input when it fits a smaller power of two (cross-GPU merges fold a few dozen keys)
     int P = MERGE_P;
@@ -55,7 +81,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(MergeParams p
         for (uint64_t i = tid; i < chunk; i += MERGE_THREADS) {
             uint64_t g = pos + i;
             uint32_t l = (uint32_t)(g / p.list_len), s = (uint32_t)(g - (uint64_t)l * p.list_len);
-            uint64_t key = base[(size_t)l * p.list_stride + s];
+            uint64_t key = __ldcg(base + (size_t)l * p.list_stride + s);  // L2: peer GPUs may have just written it
             if (key > kth) {
                 int slot = atomicAdd(&s_fill, 1);
                 sbuf[slot] = key;
@@ -78,23 +104,40 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(MergeParams p
     }
     __syncthreads();
     const int have = s_fill;
-    for (uint32_t i = tid; i < p.k; i += MERGE_THREADS) p.out[(size_t)q * p.k + i] = (int)i < have ? sbuf[i] : 0ull;
+    for (uint32_t i = tid; i < p.k; i += MERGE_THREADS) {
+        const uint64_t key = (int)i < have ? sbuf[i] : 0ull;
+        if (p.out) p.out[(size_t)q * p.k + i] = key;
+        if (p.dec_idx) {
+            float sc = key_score(key);
+            if (p.dec_metric == NK_METRIC_EUCLIDEAN) sc = sqrtf(fmaxf(-sc, 0.0f));
+            p.dec_idx[(size_t)q * p.k + i] = key ? key_row(key) : 0xffffffffu;
+            p.dec_score[(size_t)q * p.k + i] = key ? sc : 0.0f;
+        }
+    }
 }
 
 int merge_keys(const uint64_t *keys, uint32_t n_lists, size_t list_stride, size_t q_stride, uint32_t Q, uint32_t k,
-               uint64_t *out_keys, cudaStream_t stream, const int *only_if, uint32_t list_len) {
+               uint64_t *out_keys, cudaStream_t stream, const int *only_if, uint32_t list_len, uint32_t *dec_idx, float *dec_score,
+               int dec_metric, const uint32_t *wait_flags, uint32_t wait_epoch, int *wait_err) {
     if (Q == 0 || k == 0) return 0;
     if (k > MERGE_P / 2) {
         set_error("merge: k=%u too large", k);
         return -1;
     }
-    MergeParams p{keys, n_lists, list_stride, q_stride, k, out_keys, only_if, list_len ? list_len : k};
+    if (wait_flags && n_lists > MERGE_THREADS) {
+        set_error("merge: too many peers");
+        return -1;
+    }
+    MergeParams p{keys, n_lists, list_stride, q_stride, k, out_keys, only_if, list_len ? list_len : k, dec_idx, dec_score, dec_metric,
+                  wait_flags, wait_epoch, wait_err};
     merge_keys_kernel<<<Q, MERGE_THREADS, 0, stream>>>(p);
     NK_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-__global__ void decode_keys_kernel(const uint64_t *keys, size_t total, int metric, uint32_t *out_idx, float *out_score) {
+__global__ void decode_keys_kernel(const uint64_t *keys, size_t total, int metric, uint32_t *out_idx, float *out_score,
+                                   const int *only_if) {
+    if (only_if && *only_if == 0) return;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     uint64_t key = keys[i];
@@ -105,10 +148,10 @@ __global__ void decode_keys_kernel(const uint64_t *keys, size_t total, int metri
 }
 
 int decode_keys(const uint64_t *keys, uint32_t Q, uint32_t k, int metric, uint32_t *out_idx, float *out_score,
-                cudaStream_t stream) {
+                cudaStream_t stream, const int *only_if) {
     size_t total = (size_t)Q * k;
     if (total == 0) return 0;
-    decode_keys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(keys, total, metric, out_idx, out_score);
+    decode_keys_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(keys, total, metric, out_idx, out_score, only_if);
     NK_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -156,12 +199,85 @@ __global__ void __launch_bounds__(TOPK_THREADS) topk_scores_kernel(const float *
     for (uint32_t i = threadIdx.x; i < k; i += TOPK_THREADS) partial[(size_t)blockIdx.x * k + i] = sbuf[i];
 }
 
+// Top-k over an array of ready-made keys (0 = empty): the node-level selection of the best-of-chunks search
+// (group_best fills one key per node).  Same threshold + buffer + prune scheme as topk_scores_kernel.
+__global__ void __launch_bounds__(TOPK_THREADS) topk_keys_kernel(const unsigned long long *keys, uint32_t n, uint32_t k, int P,
+                                                                 uint64_t *cand, uint64_t *partial, int *flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *sbuf = reinterpret_cast<uint64_t *>(smem_raw);
+    __shared__ float s_tau;
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) {
+        s_tau = -INFINITY;
+        s_cnt = 0;
+    }
+    __syncthreads();
+    uint64_t *my = cand + (size_t)blockIdx.x * P;
+    const uint32_t num_iv = (n + TOPK_IV - 1) / TOPK_IV;
+    for (uint32_t iv = blockIdx.x; iv < num_iv; iv += gridDim.x) {
+        for (uint32_t i = iv * TOPK_IV + threadIdx.x; i < (iv + 1) * TOPK_IV && i < n; i += TOPK_THREADS) {
+            const uint64_t key = keys[i];
+            if (key && key_score(key) >= s_tau) {
+                int pos = atomicAdd(&s_cnt, 1);
+                if (pos < P) my[pos] = key;
+                else atomicExch(flags, 1);
+            }
+        }
+        __syncthreads();
+        bool need = s_cnt > P - TOPK_IV;
+        __syncthreads();
+        if (need) block_prune(my, P, &s_cnt, &s_tau, k, sbuf, P);
+    }
+    block_prune(my, P, &s_cnt, &s_tau, k, sbuf, P);
+    for (uint32_t i = threadIdx.x; i < k; i += TOPK_THREADS) partial[(size_t)blockIdx.x * k + i] = sbuf[i];
+}
+// keys [k] -> (group, row, score): group = group_of_row[row - row_base]
+__global__ void decode_group_keys_kernel(const uint64_t *keys, uint32_t k, int metric, const uint32_t *group, uint64_t row_base,
+                                         uint32_t *out_group, uint32_t *out_row, float *out_score) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k) return;
+    const uint64_t key = keys[i];
+    float s = key_score(key);
+    if (metric == NK_METRIC_EUCLIDEAN) s = sqrtf(fmaxf(-s, 0.0f));
+    const uint32_t row = key_row(key);
+    out_group[i] = key ? group[row - (uint32_t)row_base] : 0xffffffffu;
+    out_row[i] = key ? row : 0xffffffffu;
+    out_score[i] = key ? s : 0.0f;
+}
+
 __global__ void update_below_kernel(const uint64_t *keys, uint32_t Q, uint32_t k, uint64_t *below) {
     uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q < Q) below[q] = keys[(size_t)q * k + k - 1];  // 0 when the pass ran dry: nothing is below key 0
 }
 int update_below(const uint64_t *keys, uint32_t Q, uint32_t k, uint64_t *below, cudaStream_t s) {
     update_below_kernel<<<(Q + 127) / 128, 128, 0, s>>>(keys, Q, k, below);
+    NK_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int topk_keys(const DeviceInfo &di, const unsigned long long *keys, uint32_t n, uint32_t k, Workspace &ws, uint64_t *out_keys,
+              cudaStream_t s) {
+    if (n == 0 || k == 0) return 0;
+    if (k > NK_MAX_K) {
+        set_error("k=%u exceeds NK_MAX_K=%u", k, NK_MAX_K);
+        return -1;
+    }
+    int P = (int)next_pow2(k + TOPK_IV + 1);
+    uint32_t num_iv = (n + TOPK_IV - 1) / TOPK_IV;
+    uint32_t grid = (uint32_t)di.num_sms * 2;
+    if (grid > num_iv) grid = num_iv;
+    if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)grid * P * 8)) return -1;
+    if (ws_reserve((void **)&ws.partial, &ws.partial_bytes, (size_t)grid * k * 8)) return -1;
+    size_t smem = (size_t)P * 8;
+    NK_CUDA_OK(cudaFuncSetAttribute(topk_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    topk_keys_kernel<<<grid, TOPK_THREADS, smem, s>>>(keys, n, k, P, ws.cand, ws.partial, ws.flags);
+    NK_CUDA_OK(cudaGetLastError());
+    return merge_keys(ws.partial, grid, k, 0, 1, k, out_keys, s);
+}
+int decode_group_keys(const uint64_t *keys, uint32_t k, int metric, const uint32_t *group, uint64_t row_base, uint32_t *out_group,
+                      uint32_t *out_row, float *out_score, cudaStream_t s) {
+    if (k == 0) return 0;
+    decode_group_keys_kernel<<<(k + 127) / 128, 128, 0, s>>>(keys, k, metric, group, row_base, out_group, out_row, out_score);
     NK_CUDA_OK(cudaGetLastError());
     return 0;
 }

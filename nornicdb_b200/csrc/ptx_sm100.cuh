@@ -87,6 +87,10 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// kind::f16 with FP16 operands: a_format = b_format = 0 (F16), fp32 accumulate.
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 // Shared-memory matrix descriptor, K-major operand in the 128-byte-swizzle layout TMA writes
 // (rows of 128 B, 8-row groups 1024 B apart): start>>4 [0,14), LBO=1 [16,30), SBO=64 [32,46),
 // version=1 [46,48), layout SWIZZLE_128B=2 [61,64).

@@ -44,7 +44,7 @@ int ws_reserve(void **p, size_t *cur, size_t need) {
 }
 
 int Workspace::release() {
-    void *ptrs[] = {cand, partial, keys, keys2, below, queries, out_idx, out_score, qaux, rownorm, flags};
+    void *ptrs[] = {cand, partial, keys, keys2, below, queries, out_idx, out_score, qaux, rownorm, flags, sub_rows, sub_gather, scratch};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     *this = Workspace();

@@ -17,6 +17,10 @@
 //   * each CTA finally emits its best k keys per query; merge_keys() folds the per-CTA lists.
 //
 // Algorithmic HBM traffic per launch = n*dim*sizeof(elem) (+ QT*dim*4 of queries): DESIGN.md §Kernels.
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "kernels.cuh"
 
 namespace nk {
@@ -39,6 +43,7 @@ struct SimtParams {
     const int *only_if;  // device-side conditional fallback: run only if *only_if != 0
     const uint64_t *below;  // per-query exclusive key bound (k > NK_MAX_K passes) or nullptr
     const uint32_t *mask;   // row bitmask or nullptr
+    float min_score;        // caller's score floor (key space); -inf = none
 };
 
 // ---- element loaders -------------------------------------------------------------------------
@@ -62,6 +67,23 @@ template <> struct Lane<__half, true> {
         f = __half22float2(*reinterpret_cast<__half2 *>(&w2)); x[4] = f.x; x[5] = f.y;
         f = __half22float2(*reinterpret_cast<__half2 *>(&w3)); x[6] = f.x; x[7] = f.y;
     }
+};
+template <> struct Lane<__nv_bfloat16, true> {
+    static constexpr int EPL = 8;
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&x)[8]) {
+        uint32_t w[4];
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // bf16 -> fp32 is a 16-bit shift
+            x[2 * i] = __uint_as_float(w[i] << 16);
+            x[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+};
+template <> struct Lane<__nv_bfloat16, false> {
+    static constexpr int EPL = 1;
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&x)[1]) { x[0] = __bfloat162float(*p); }
 };
 template <> struct Lane<float, false> {
     static constexpr int EPL = 1;
@@ -121,7 +143,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) knn_scan_simt_kernel(SimtParams 
         qs[i] = qi < p.nq ? p.queries[(size_t)(p.q0 + qi) * dim + j] : 0.0f;
     }
     if (tid < QT) {
-        s_tau[tid] = -INFINITY;
+        s_tau[tid] = p.min_score;
         s_cnt[tid] = 0;
     }
     __syncthreads();
@@ -219,7 +241,7 @@ __global__ void __launch_bounds__(SIMT_THREADS) knn_scan_simt_kernel(SimtParams 
                     s = den > 0.0f ? s / den : 0.0f;
                 }
                 if (s != s) s = -INFINITY;
-                if (s >= s_tau[qi]) {
+                if (s >= s_tau[qi] && s >= p.min_score) {  // (a prune with fewer than k live keys resets tau to -inf)
                     const uint64_t key = make_key(s, (uint32_t)(p.row_base + row));
                     if (!p.below || key < p.below[p.q0 + qi]) {
                         int pos = atomicAdd(&s_cnt[qi], 1);
@@ -277,8 +299,38 @@ static SimtKernel pick_kernel(int dtype, bool vec, bool euclid, int qt) {
         if (vec) return euclid ? pick_qt<__half, true, true>(qt) : pick_qt<__half, true, false>(qt);
         return euclid ? pick_qt<__half, false, true>(qt) : pick_qt<__half, false, false>(qt);
     }
+    if (dtype == NK_DTYPE_BF16) {
+        if (vec) return euclid ? pick_qt<__nv_bfloat16, true, true>(qt) : pick_qt<__nv_bfloat16, true, false>(qt);
+        return euclid ? pick_qt<__nv_bfloat16, false, true>(qt) : pick_qt<__nv_bfloat16, false, false>(qt);
+    }
     if (vec) return euclid ? pick_qt<float, true, true>(qt) : pick_qt<float, true, false>(qt);
     return euclid ? pick_qt<float, false, true>(qt) : pick_qt<float, false, false>(qt);
+}
+
+// cudaFuncSetAttribute + occupancy query once per (kernel, device, smem) instead of once per search
+static std::mutex g_simt_mu;
+static std::map<std::tuple<const void *, int, size_t>, int> g_simt_occ;
+static std::map<std::pair<const void *, int>, size_t> g_simt_smem;
+static int simt_ensure(const void *kern, int device, size_t smem) {
+    std::lock_guard<std::mutex> lk(g_simt_mu);
+    size_t &cur = g_simt_smem[{kern, device}];
+    if (cur < smem || cur == 0) {
+        NK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
+    return 0;
+}
+static int simt_occupancy(const void *kern, int device, size_t smem) {
+    std::lock_guard<std::mutex> lk(g_simt_mu);
+    auto key = std::make_tuple(kern, device, smem);
+    auto it = g_simt_occ.find(key);
+    if (it != g_simt_occ.end()) return it->second;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SIMT_THREADS, smem) != cudaSuccess) { cudaGetLastError(); occ = 1; }
+    if (occ < 1) occ = 1;
+    if (occ > 8) occ = 8;
+    g_simt_occ[key] = occ;
+    return occ;
 }
 
 int simt_cap_for_k(uint32_t k) {
@@ -292,8 +344,8 @@ int scan_simt(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *
         set_error("k=%u exceeds NK_MAX_K=%u", a.k, NK_MAX_K);
         return -1;
     }
-    const size_t esz = a.dtype == NK_DTYPE_F16 ? 2 : 4;
-    const uint32_t vec_elems = a.dtype == NK_DTYPE_F16 ? 8 : 4;
+    const size_t esz = a.dtype == NK_DTYPE_F32 ? 4 : 2;
+    const uint32_t vec_elems = a.dtype == NK_DTYPE_F32 ? 4 : 8;
     const bool vec = (a.dim % vec_elems == 0) && ((reinterpret_cast<uintptr_t>(a.rows) & 15) == 0);
     const bool euclid = a.metric == NK_METRIC_EUCLIDEAN;
     const int P = simt_cap_for_k(a.k);
@@ -316,11 +368,8 @@ int scan_simt(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *
             return -1;
         }
         SimtKernel kern = pick_kernel(a.dtype, vec, euclid, qt);
-        NK_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 0;
-        NK_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SIMT_THREADS, smem));
-        if (occ < 1) occ = 1;
-        if (occ > 8) occ = 8;
+        if (simt_ensure(reinterpret_cast<const void *>(kern), di.device_id, smem)) return -1;
+        int occ = simt_occupancy(reinterpret_cast<const void *>(kern), di.device_id, smem);
         // One grid for every query group of this search so the per-CTA partial lists line up.
         if (grid_used == 0) {
             grid_used = (uint32_t)di.num_sms * (uint32_t)occ;
@@ -332,7 +381,7 @@ int scan_simt(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *
         SimtParams p;
         p.rows = a.rows; p.n = a.n; p.dim = a.dim; p.row_base = a.row_base;
         p.queries = a.queries; p.q0 = q0; p.nq = left < (uint32_t)qt ? left : (uint32_t)qt; p.k = a.k;
-        p.metric = a.metric; p.P = P; p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = a.only_if; p.below = a.below; p.mask = a.row_mask;
+        p.metric = a.metric; p.P = P; p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = a.only_if; p.below = a.below; p.mask = a.row_mask; p.min_score = a.min_score;
         kern<<<grid_used, SIMT_THREADS, smem, a.stream>>>(p);
         NK_CUDA_OK(cudaGetLastError());
         if (launches) ++*launches;
@@ -341,7 +390,10 @@ int scan_simt(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *
     }
     if (a.ev_end) NK_CUDA_OK(cudaEventRecord(a.ev_end, a.stream));
     // Fold the per-CTA lists: list l of query q starts at partial[(q*grid + l)*k].
-    if (merge_keys(ws.partial, grid_used, a.k, (size_t)grid_used * a.k, a.Q, a.k, out_keys, a.stream, a.only_if)) return -1;
+    // ... and, when the caller wants them, the decoded (index, score) arrays in the same launch
+    if (merge_keys(ws.partial, grid_used, a.k, (size_t)grid_used * a.k, a.Q, a.k, out_keys, a.stream, a.only_if, 0, a.out_idx, a.out_score,
+                   a.metric))
+        return -1;
     if (launches) ++*launches;
     return 0;
 }

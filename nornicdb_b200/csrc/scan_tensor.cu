@@ -37,6 +37,11 @@
 // Algorithmic HBM traffic per launch: n*dim*4 (corpus, once); query re-reads are served from L2.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
 
 #include "kernels.cuh"
 #include "ptx_sm100.cuh"
@@ -85,34 +90,197 @@ __device__ long long g_tc_prof[32];
 #define TC_PROF_BEGIN() long long _t0 = prof ? clock64() : 0
 #define TC_PROF_END(slot) do { if (prof) { long long _t1 = clock64(); acc_##slot += _t1 - _t0; } } while (0)
 
-// Queries -> tf32 hi (/ lo) arrays, zero padded to a multiple of 64 rows; cosine normalises first; also |q|.
-__global__ void tc_prep_queries_kernel(const float *q, uint32_t Q, uint32_t dim, int normalise, float *qhi, float *qlo,
-                                       float *qnorm) {
+// Exact fp32 score of one corpus row against the query staged in shared memory, by one warp: the arithmetic every
+// filter path re-scores its survivors with (fp32 FMA, 128-bit loads; fp16 rows are widened exactly).  Returns the key
+// score: dot | dot / sqrt(|x|^2 |q|^2) (0 for zero vectors, simd_amd64.go:31-35) | -|x - q|^2; NaN -> -inf.  *xx_out = |x|^2.
+__device__ __forceinline__ float warp_exact_score(const void *rows, int dtype, size_t local, uint32_t dim, const float *qs, float qq,
+                                                  int metric, int lane, float *xx_out = nullptr) {
+    float d = 0.0f, xx = 0.0f;
+    const float4 *q4 = reinterpret_cast<const float4 *>(qs);
+    auto acc4 = [&](const float4 v, const float4 u) {
+        if (metric == NK_METRIC_EUCLIDEAN) {
+            float t;
+            t = v.x - u.x; d = fmaf(t, t, d);
+            t = v.y - u.y; d = fmaf(t, t, d);
+            t = v.z - u.z; d = fmaf(t, t, d);
+            t = v.w - u.w; d = fmaf(t, t, d);
+            xx = fmaf(v.x, v.x, xx); xx = fmaf(v.y, v.y, xx); xx = fmaf(v.z, v.z, xx); xx = fmaf(v.w, v.w, xx);
+        } else {
+            d = fmaf(v.x, u.x, d); xx = fmaf(v.x, v.x, xx);
+            d = fmaf(v.y, u.y, d); xx = fmaf(v.y, v.y, xx);
+            d = fmaf(v.z, u.z, d); xx = fmaf(v.z, v.z, xx);
+            d = fmaf(v.w, u.w, d); xx = fmaf(v.w, v.w, xx);
+        }
+    };
+    if (dtype == NK_DTYPE_F32) {
+        const float4 *x4 = reinterpret_cast<const float4 *>(static_cast<const float *>(rows) + local * dim);
+#pragma unroll 8
+        for (uint32_t j = lane; j < dim / 4; j += 32) acc4(__ldg(x4 + j), q4[j]);
+    } else {  // fp16 rows, dim % 8 == 0: 8 halves per 128-bit load
+        const uint4 *x8 = reinterpret_cast<const uint4 *>(static_cast<const __half *>(rows) + local * dim);
+#pragma unroll 4
+        for (uint32_t j = lane; j < dim / 8; j += 32) {
+            const uint4 w = __ldg(x8 + j);
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&w.x)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&w.y));
+            const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&w.z)), f3 = __half22float2(*reinterpret_cast<const __half2 *>(&w.w));
+            acc4(make_float4(f0.x, f0.y, f1.x, f1.y), q4[2 * j]);
+            acc4(make_float4(f2.x, f2.y, f3.x, f3.y), q4[2 * j + 1]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        d += __shfl_xor_sync(0xffffffffu, d, o);
+        xx += __shfl_xor_sync(0xffffffffu, xx, o);
+    }
+    float sc = d;
+    if (metric == NK_METRIC_EUCLIDEAN) sc = -d;
+    else if (metric == NK_METRIC_COSINE) {
+        const float den = sqrtf(xx * qq);
+        sc = den > 0.0f ? d / den : 0.0f;
+    }
+    if (sc != sc) sc = -INFINITY;
+    if (xx_out) *xx_out = xx;
+    return sc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// filter_prep_kernel — everything a filter search needs before its scan, in ONE launch (one CTA per padded query row):
+//   * |q|, cosine normalisation; TF32 hi / lo split (TF32 filter + exact 3xTF32 stages); BF16 copy with the measured
+//     rounding residues qa = |bf16(q)|, qb = |q - bf16(q)| + acc_c |q| (shadow stage);
+//   * clears the search state the scan kernels accumulate into (shared thresholds, list fills, status words 1..7) —
+//     previously two cudaMemsetAsync;
+//   * SAMPLED INITIAL THRESHOLD: the query's exact fp32 score against `sample` evenly spaced rows of the shard; the k-th
+//     largest of their LOWER bounds (score minus the fp32 summation allowance) is a lower bound of the true k-th best
+//     score, so the scan starts with a real threshold instead of buffering every (row, query) pair of its first two
+//     tiles and pruning 64-128 full buffers per CTA (~25 us per launch, the largest fixed cost of a small-shard search).
+// ---------------------------------------------------------------------------------------------------
+constexpr int PREP_THREADS = 256;
+struct PrepParams {
+    const float *q;
+    uint32_t Q, dim, dimpad;
+    int normalise, metric;
+    float acc_c;
+    float *qhi, *qlo;      // [Qpad x dim] (nullable)
+    uint16_t *qbf;         // [Qpad x dimpad] (nullable); fp16 bits when qbf_f16
+    int qbf_f16;
+    float *qnorm, *qa, *qb;
+    uint32_t *state;       // gtau[QA] then gcount[QA]
+    uint32_t Qpad, QA;
+    int *flags;
+    // sampled initial threshold (sample == 0: none)
+    const void *rows;
+    int dtype;
+    uint32_t n, sample, k;
+    const uint32_t *mask;
+    float min_score;
+    const int *only_if;
+};
+
+__global__ void __launch_bounds__(PREP_THREADS) filter_prep_kernel(PrepParams p) {
+    extern __shared__ __align__(16) unsigned char prep_smem[];
+    float *qs = reinterpret_cast<float *>(prep_smem);                                  // raw query [dim]
+    uint64_t *skeys = reinterpret_cast<uint64_t *>(prep_smem + (size_t)((p.dim + 3) & ~3u) * 4);  // [sample]
+    __shared__ float red[3][PREP_THREADS / 32];
+    if (p.only_if && *p.only_if == 0) return;
     const uint32_t row = blockIdx.x;
-    __shared__ float red[32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    constexpr int NW = PREP_THREADS / 32;
+    // ---- clear the search state: own entry, block 0 also the padding and the status words
+    if (p.state) {
+        if (tid == 0) { p.state[row] = 0u; p.state[p.QA + row] = 0u; }
+        if (row == 0) {
+            for (uint32_t i = p.Qpad + tid; i < p.QA; i += PREP_THREADS) { p.state[i] = 0u; p.state[p.QA + i] = 0u; }
+            if (tid >= 1 && tid <= 7) p.flags[tid] = 0;
+        }
+    }
     float t = 0.0f;
-    if (row < Q) {
+    if (row < p.Q) {
         float a = 0.0f;
-        for (uint32_t j = threadIdx.x; j < dim; j += blockDim.x) a = fmaf(q[(size_t)row * dim + j], q[(size_t)row * dim + j], a);
+        for (uint32_t j = tid; j < p.dim; j += PREP_THREADS) {
+            const float v = p.q[(size_t)row * p.dim + j];
+            qs[j] = v;
+            a = fmaf(v, v, a);
+        }
 #pragma unroll
         for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
-        __syncthreads();
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        if (lane == 0) red[0][w] = a;
     }
+    __syncthreads();
+    if (row < p.Q)
+        for (int i = 0; i < NW; ++i) t += red[0][i];
     const float nrm = sqrtf(t);
     // zero query -> all cosine scores 0 (simd_amd64.go:31-35)
-    const float inv = normalise ? (t > 0.0f ? 1.0f / nrm : 0.0f) : 1.0f;
-    if (threadIdx.x == 0 && qnorm) qnorm[row] = normalise ? (t > 0.0f ? 1.0f : 0.0f) : nrm;
-    for (uint32_t j = threadIdx.x; j < dim; j += blockDim.x) {
-        float v = row < Q ? q[(size_t)row * dim + j] * inv : 0.0f;
-        float h = __uint_as_float(ptx::tf32_round_bits(__float_as_uint(v)));
-        qhi[(size_t)row * dim + j] = h;
-        if (qlo) qlo[(size_t)row * dim + j] = v - h;
+    const float inv = p.normalise ? (t > 0.0f ? 1.0f / nrm : 0.0f) : 1.0f;
+    const float qn = p.normalise ? (t > 0.0f ? 1.0f : 0.0f) : nrm;
+    if (p.qhi) {
+        for (uint32_t j = tid; j < p.dim; j += PREP_THREADS) {
+            const float v = row < p.Q ? qs[j] * inv : 0.0f;
+            const float h = __uint_as_float(ptx::tf32_round_bits(__float_as_uint(v)));
+            p.qhi[(size_t)row * p.dim + j] = h;
+            if (p.qlo) p.qlo[(size_t)row * p.dim + j] = v - h;
+        }
+    }
+    float hh = 0.0f, dd = 0.0f;
+    if (p.qbf) {
+        for (uint32_t j = tid; j < p.dimpad; j += PREP_THREADS) {
+            const float v = (row < p.Q && j < p.dim) ? qs[j] * inv : 0.0f;
+            uint16_t b;
+            float vb;
+            if (p.qbf_f16) {
+                const __half h = __float2half_rn(v);
+                b = __half_as_ushort(h);
+                vb = __half2float(h);
+            } else {
+                b = ptx::f32_to_bf16_bits(v);
+                vb = __uint_as_float((uint32_t)b << 16);
+            }
+            p.qbf[(size_t)row * p.dimpad + j] = b;
+            hh = fmaf(vb, vb, hh);
+            dd = fmaf(v - vb, v - vb, dd);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            hh += __shfl_xor_sync(0xffffffffu, hh, o);
+            dd += __shfl_xor_sync(0xffffffffu, dd, o);
+        }
+        if (lane == 0) { red[1][w] = hh; red[2][w] = dd; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (p.qnorm) p.qnorm[row] = qn;
+        if (p.qbf) {
+            hh = dd = 0.0f;
+            for (int i = 0; i < NW; ++i) { hh += red[1][i]; dd += red[2][i]; }
+            p.qa[row] = sqrtf(hh) * 1.0001f;
+            p.qb[row] = (sqrtf(dd) + p.acc_c * qn) * 1.0001f;
+        }
+    }
+    // ---- sampled initial threshold
+    if (p.sample == 0 || row >= p.Q) return;
+    const uint32_t S = p.sample;  // power of two
+    for (uint32_t i = w; i < S; i += NW) {
+        uint64_t key = 0ull;
+        const uint64_t r = p.n >= S ? (uint64_t)i * p.n / S : i;
+        if (r < p.n && (!p.mask || ((__ldg(p.mask + (r >> 5)) >> (r & 31)) & 1u))) {
+            float xx;
+            const float sc = warp_exact_score(p.rows, p.dtype, (size_t)r, p.dim, qs, t, p.metric, lane, &xx);
+            // lower bound of the real-valued score: the fp32 summation allowance the filters use (acc_c |x||q|)
+            float lo = sc - (p.metric == NK_METRIC_COSINE ? p.acc_c : p.metric == NK_METRIC_DOT ? p.acc_c * sqrtf(xx * t) : p.acc_c * -sc);
+            if (lo == lo && lo > -INFINITY) key = (uint64_t)ord_bits(lo);
+        }
+        if (lane == 0) skeys[i] = key;
+    }
+    block_bitonic_sort_desc(skeys, (int)S);  // starts with a __syncthreads
+    if (tid == 0 && p.k <= S) {
+        const uint64_t kth = skeys[p.k - 1];
+        if (kth) {  // at least k live sampled rows
+            const float tau0 = fmaxf(ord_to_float((uint32_t)kth), p.min_score);
+            if (tau0 > -INFINITY) p.state[row] = ord_bits(tau0);
+        }
     }
 }
 
-template <int NT, int QT>
+template <int NT, int QT, bool DUMP>
 __global__ void __launch_bounds__(tc::THREADS, 1)
 knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_qhi,
                    const __grid_constant__ CUtensorMap map_qlo, tc::Params p) {
@@ -157,7 +325,14 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
     }
     if (warp == 2) ptx::tmem_alloc(&sh.tmem_base, TMEM_COLS);
     if (tid < QT) {
-        sh.tau[tid] = -INFINITY;
+        // start threshold: the caller's score floor and, when the prep kernel sampled the shard, a lower bound of the
+        // query's k-th best score (no flood tiles then)
+        float t0 = p.min_score;
+        if (FILTER && p.presampled && (uint32_t)tid < nq) {
+            const uint32_t g = __ldcg(p.gtau + q0 + tid);
+            if (g) t0 = fmaxf(t0, ord_to_float(g));
+        }
+        sh.tau[tid] = t0;
         sh.cnt[tid] = 0;
         sh.qn[tid] = (FILTER && p.qnorm) ? p.qnorm[qpad_off + tid] : 1.0f;
     }
@@ -165,6 +340,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = sh.tmem_base;
+    const bool flood = !(FILTER && p.presampled);  // first two tiles: every (row, query) pair is placed directly
 
     if (warp == 0) {
         // ===================================== TMA producer: corpus slabs ========================
@@ -317,7 +493,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                 if (cosine) mul = x2 > 0.0f ? 1.0f / xn : 0.0f;
                 if (FILTER) {
                     bnd = cosine ? p.margin_c : bfac * xn;
-                    if (!cosine && alive) atomicMax(&sh.maxxx, __float_as_uint(x2));
+                    if (!cosine && alive && x2 < INFINITY) atomicMax(&sh.maxxx, __float_as_uint(x2));  // NaN / Inf rows: kept, judged exactly
                     if (euclid) mul = 2.0f;
                 }
 #pragma unroll 1
@@ -334,7 +510,22 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                         __syncwarp();
                         if (lane == 0) ptx::mbar_arrive(&sh.accempty[m]);
                     }
-                    if (it < 2 && cb < nq) {
+                    if (DUMP && FILTER && row < p.n) {  // tests only: score estimate and error bound per (row, query)
+                        for (uint32_t c = 0; c < 64 && cb + c < nq; ++c) {
+                            uint32_t bits = 0;
+#pragma unroll
+                            for (uint32_t i = 0; i < 32; ++i) {
+                                if (c == i) bits = v0[i];
+                                if (c == 32 + i) bits = v1[i];
+                            }
+                            const float qn = sh.qn[cb + c];
+                            float est = __uint_as_float(bits) * mul, b = bnd * qn;
+                            if (euclid) { est -= fmaf(qn, qn, x2); b += EUC_EPS * fmaf(qn, qn, x2); }
+                            p.dump_est[(size_t)row * p.dump_ld + q0 + cb + c] = est;
+                            p.dump_bnd[(size_t)row * p.dump_ld + q0 + cb + c] = b;
+                        }
+                    }
+                    if (flood && it < 2 && cb < nq) {
                         // Flood tiles: until the first prune (after this CTA's second tile) every threshold is -inf and
                         // EVERY (row, query) pair is buffered.  Place them directly - slot = tile-local row, no atomics,
                         // no register select - instead of 256 x QT trips through the rare-push loop (~60 us per launch).
@@ -353,7 +544,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
                                 } else if (sc != sc) {
                                     sc = -INFINITY;
                                 }
-                                my_cand[(size_t)qi * P + slot] = alive ? make_key(sc, grow) : 0ull;  // 0 = empty slot
+                                my_cand[(size_t)qi * P + slot] = (alive && sc >= p.min_score) ? make_key(sc, grow) : 0ull;  // 0 = empty slot
                             }
                         }
                         if (rt == 0 && half == 0)
@@ -412,12 +603,13 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
             for (uint32_t qi = quad; qi < nq; qi += 4)
                 if (sh.cnt[qi] > prune_at) {
                     const float margin2 = !FILTER ? 0.0f : filter_margin2(p.metric, p.margin_c, __uint_as_float(sh.maxxx), sh.qn[qi]);
-                    float floor_tau = -INFINITY;
+                    float floor_tau = p.min_score;
                     if (FILTER) {
                         const uint32_t g = __ldcg(p.gtau + q0 + qi);
-                        if (g) floor_tau = ord_to_float(g);
+                        if (g) floor_tau = fmaxf(floor_tau, ord_to_float(g));
                     }
-                    warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, FILTER, margin2, prune_at, floor_tau);
+                    warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, FILTER, margin2, prune_at, floor_tau,
+                                   nullptr, p.flags + FLAG_OVERFLOW);
                     // everything inside the margin must fit below prune_at, or the next tile could overflow the buffer
                     if (FILTER && lane == 0 && sh.cnt[qi] >= prune_at) atomicOr(p.flags + 1, 1);
                     // publish: this CTA's threshold is a lower bound on the true global k-th best score, so every CTA
@@ -444,18 +636,29 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
             const float margin2 = !FILTER ? 0.0f : filter_margin2(p.metric, p.margin_c, __uint_as_float(sh.maxxx), sh.qn[qi]);
             if (FILTER) {
                 // survivors (inside this CTA's margin AND above the shared threshold) go to the query's shared list
-                float floor_tau = -INFINITY;
+                float floor_tau = p.min_score;
                 const uint32_t g = __ldcg(p.gtau + q0 + qi);
-                if (g) floor_tau = ord_to_float(g);
+                if (g) floor_tau = fmaxf(floor_tau, ord_to_float(g));
+                if (sh.cnt[qi] <= (int)p.k_emit) {
+                    // few entries: no local selection, the finish kernel selects globally — append what still reaches the
+                    // current threshold
+                    const float t = fmaxf(sh.tau[qi], floor_tau);
+                    uint64_t thr = t > -INFINITY ? (uint64_t)ord_bits(t) << 32 : 1ull;
+                    if (thr == 0ull) thr = 1ull;
+                    warp_emit_above(my_cand + (size_t)qi * P, sh.cnt[qi], thr, lane, p.partial + (size_t)(q0 + qi) * p.list_cap,
+                                    (int)p.list_cap, p.gcount + q0 + qi);
+                    continue;
+                }
                 warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane,
                                p.partial + (size_t)(q0 + qi) * p.list_cap, (int)p.list_cap, true, margin2,
-                               (int)p.k_emit, floor_tau, p.gcount + q0 + qi);
+                               (int)p.k_emit, floor_tau, p.gcount + q0 + qi, p.flags + FLAG_OVERFLOW);
                 // the list was cut at k_emit while rows inside the margin remained -> exact fallback
-                if (lane == 0 && sh.cnt[qi] >= (int)p.k_emit && (int)p.k_emit > (int)p.k) atomicOr(p.flags + 1, 2);
+                if (lane == 0 && sh.cnt[qi] >= (int)p.k_emit && (int)p.k_emit > (int)p.k) atomicOr(p.flags + FLAG_OVERFLOW, 2);
                 if (lane == 0 && sh.tau[qi] > -INFINITY) atomicMax(p.gtau + q0 + qi, ord_bits(sh.tau[qi]));
             } else {
                 warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane,
-                               p.partial + ((size_t)(q0 + qi) * gridDim.x + blockIdx.x) * p.k_emit, (int)p.k_emit, false, 0.0f, (int)p.k_emit);
+                               p.partial + ((size_t)(q0 + qi) * gridDim.x + blockIdx.x) * p.k_emit, (int)p.k_emit, false, 0.0f, (int)p.k_emit,
+                               p.min_score);
             }
         }
         if (FILTER && !cosine && tid == 0) atomicMax(reinterpret_cast<unsigned int *>(p.flags + 2), sh.maxxx);
@@ -470,16 +673,21 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
 
 // ---------------------------------------------------------------------------------------------------
 // Filter-mode finish (one CTA per query): the query's shared list holds every row whose upper bound reached the
-// cross-CTA threshold (k plus a few dozen).  Sort it by bound; everything with bound >= (k-th bound - 2*Bmax) may belong
-// to the true top-k: those rows are re-scored EXACTLY in fp32 with the same arithmetic as the CUDA-core scan
-// (dot / sqrt(|x|^2 |q|^2) etc.), sorted by (score desc, row asc), and the best k written out.  A list longer than
-// FINISH_CAP (tiny shards with large k, or adversarial near-ties) raises the overflow flag; the exact kernels queued
-// behind redo the search.
+// cross-CTA threshold (k plus a few dozen).  Radix-select the k-th largest bound; everything with bound >= (k-th bound -
+// 2*Bmax) may belong to the true top-k: those rows are re-scored EXACTLY in fp32 with the same arithmetic as the
+// CUDA-core scan (dot / sqrt(|x|^2 |q|^2) etc.), sorted by (score desc, row asc), and the best k written out — as keys
+// and, when the caller wants them, already decoded (index, score), so no separate decode launch follows.  Survivor
+// sets of any size are handled in rounds of FINISH_WIN list entries (near-tie data: thousands of rows inside the margin)
+// with the running best k carried from round to round.
+// The LAST CTA to finish does the stage bookkeeping that used to be two more launches: it turns the stage's overflow
+// flag into the retry marker and, if a retry is due, wipes the shared thresholds and list fills.
 // ---------------------------------------------------------------------------------------------------
 constexpr int FINISH_THREADS = 256;
 constexpr int FINISH_CAP = 4096;
+constexpr int FINISH_WIN = FINISH_CAP - 256;  // list entries per round; the carried best k (<= 192) fits in the rest
 struct FinishParams {
-    const void *rows;        // fp32 corpus shard
+    const void *rows;        // corpus shard (fp32, or fp16 for the fp16 tensor path)
+    int dtype;
     uint32_t dim;
     uint64_t row_base;
     const float *queries;    // raw fp32 queries [Q x dim]
@@ -488,11 +696,17 @@ struct FinishParams {
     uint32_t list_cap, k;
     int metric;
     float margin_c;          // TF32 passes: c in |s_hat - s| <= c |x||q|
-    uint32_t q_big;          // queries [0, q_big) went through the BF16 kernel: bound factors qa / qb / qn below
+    uint32_t q_big;          // queries [0, q_big) went through the BF16 / FP16 kernel: bound factors qa / qb / qn below
     const float *qa, *qb, *qn;
     int *flags;
     const int *only_if;      // retry stage: run only if *only_if != 0
-    uint64_t *out;           // [Q][k]
+    uint64_t *out;           // [Q][k] keys
+    uint32_t *out_idx;       // optional fused decode (nullable): [Q][k]
+    float *out_score;
+    float min_score;         // caller's score floor: exact scores below it are dropped
+    int mark_retry;          // first stage of a two-stage filter: overflow -> retry marker + state wipe
+    uint32_t *state;         // gtau[QA] + gcount[QA]
+    uint32_t state_words;
 };
 
 __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishParams p) {
@@ -501,13 +715,13 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
     uint64_t *se = reinterpret_cast<uint64_t *>(smem_raw + FINISH_CAP * 8);     // FINISH_CAP exact keys
     float *qs = reinterpret_cast<float *>(smem_raw + FINISH_CAP * 16);          // query
     __shared__ float s_qq;
-    __shared__ int s_count;
+    __shared__ int s_count, s_last;
     if (p.only_if && *p.only_if == 0) return;
     const uint32_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (uint32_t j = tid; j < p.dim; j += FINISH_THREADS) qs[j] = p.queries[(size_t)q * p.dim + j];
     int n = p.gcount[q];
-    if (tid == 0) atomicMax(p.flags + 7, n);  // diagnostics: longest shared list of this search
+    if (tid == 0) atomicMax(p.flags + FLAG_LONGEST, n);  // diagnostics: longest shared list of this search
     if (n > (int)p.list_cap) n = (int)p.list_cap;
     __syncthreads();
     if (warp == 0) {
@@ -518,9 +732,9 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
         if (lane == 0) s_qq = a;
     }
     __syncthreads();
-    const float maxxx = __uint_as_float((unsigned int)p.flags[2]);
-    const float margin2 = q < p.q_big ? bf16_margin2(p.metric, __uint_as_float((unsigned int)p.flags[4]), __uint_as_float((unsigned int)p.flags[6]),
-                                                     maxxx, p.qa[q], p.qb[q], p.qn[q])
+    const float maxxx = __uint_as_float((unsigned int)p.flags[FLAG_MAXXX]);
+    const float margin2 = q < p.q_big ? bf16_margin2(p.metric, __uint_as_float((unsigned int)p.flags[FLAG_MAX_RA]),
+                                                     __uint_as_float((unsigned int)p.flags[FLAG_MAX_RB]), maxxx, p.qa[q], p.qb[q], p.qn[q])
                                       : filter_margin2(p.metric, p.margin_c, maxxx, sqrtf(s_qq));
     const uint64_t *list = p.lists + (size_t)q * p.list_cap;
     // k-th largest bound by radix select over the score bits that actually vary (8 bits per pass, smem histogram; the
@@ -587,79 +801,75 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
             rem = shift;
         }
         __syncthreads();
-        thr_key = (uint64_t)ord_bits(ord_to_float(s_prefix) - margin2) << 32;
-        if (thr_key == 0ull) thr_key = 1ull;
-    }
-    for (int i = tid; i < n; i += FINISH_THREADS) {
-        const uint64_t key = __ldcg(list + i);
-        if (key >= thr_key) {
-            const int pos = atomicAdd(&s_count, 1);
-            if (pos < FINISH_CAP) sb[pos] = key;
+        const float thr = ord_to_float(s_prefix) - margin2;
+        if (thr < INFINITY) {
+            thr_key = (uint64_t)ord_bits(thr) << 32;
+            if (thr_key == 0ull) thr_key = 1ull;
+        } else if (tid == 0) {
+            // k-th bound +inf / NaN (k or more NaN rows) or a non-finite margin: no threshold can be trusted -> keep every
+            // listed row here and let the exact stage redo the search
+            atomicOr(p.flags + FLAG_OVERFLOW, 8);
         }
+    }
+    // ---- rounds: gather survivors of a window of the list, re-score them exactly, fold into the running best k
+    int carry = 0;
+    for (int w0 = 0; w0 < n || w0 == 0; w0 += FINISH_WIN) {
+        __syncthreads();
+        if (tid == 0) s_count = 0;
+        __syncthreads();
+        const int w1 = min(n, w0 + FINISH_WIN);
+        for (int i = w0 + tid; i < w1; i += FINISH_THREADS) {
+            const uint64_t key = __ldcg(list + i);
+            if (key >= thr_key) sb[atomicAdd(&s_count, 1)] = key;
+        }
+        __syncthreads();
+        const int count = s_count;  // <= FINISH_WIN
+        for (int i = warp; i < count; i += FINISH_THREADS / 32) {
+            const uint32_t grow = key_row(sb[i]);
+            const size_t local = (size_t)(grow - (uint32_t)p.row_base);
+            const float sc = warp_exact_score(p.rows, p.dtype, local, p.dim, qs, s_qq, p.metric, lane);
+            if (lane == 0) se[carry + i] = sc >= p.min_score ? make_key(sc, grow) : 0ull;
+        }
+        const int total = carry + count;
+        int P2 = 32;
+        while (P2 < total) P2 <<= 1;
+        __syncthreads();
+        for (int i = total + tid; i < P2; i += FINISH_THREADS) se[i] = 0ull;
+        block_bitonic_sort_desc(se, P2);
+        carry = total < (int)p.k ? total : (int)p.k;
+    }
+    for (uint32_t i = tid; i < p.k; i += FINISH_THREADS) {
+        const uint64_t key = (int)i < carry ? se[i] : 0ull;
+        p.out[(size_t)q * p.k + i] = key;
+        if (p.out_idx) {
+            float sc = key_score(key);
+            if (p.metric == NK_METRIC_EUCLIDEAN) sc = sqrtf(fmaxf(-sc, 0.0f));
+            p.out_idx[(size_t)q * p.k + i] = key ? key_row(key) : 0xffffffffu;
+            p.out_score[(size_t)q * p.k + i] = key ? sc : 0.0f;
+        }
+    }
+    // ---- stage bookkeeping by the last CTA
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        s_last = atomicAdd(p.flags + FLAG_FINISH_CTAS, 1) == (int)gridDim.x - 1;
     }
     __syncthreads();
-    if (s_count > FINISH_CAP) {  // thousands of rows inside the margin: adversarial near-ties -> exact fallback
-        if (tid == 0) atomicOr(p.flags + 1, 4);
+    if (!s_last) return;
+    __threadfence();
+    const int ovf = atomicOr(p.flags + FLAG_OVERFLOW, 0);
+    if (p.mark_retry) {
+        if (ovf)
+            for (uint32_t i = tid; i < p.state_words; i += FINISH_THREADS) p.state[i] = 0u;
+        if (tid == 0) {
+            p.flags[FLAG_RETRY] = ovf != 0;
+            p.flags[FLAG_OVERFLOW] = 0;
+            if (ovf) atomicAdd(p.flags + FLAG_N_RETRY, 1);
+        }
+    } else if (tid == 0 && ovf) {
+        atomicAdd(p.flags + FLAG_N_EXACT, 1);
     }
-    const int count = s_count < FINISH_CAP ? s_count : FINISH_CAP;
-    // exact scores
-    for (int i = warp; i < count; i += FINISH_THREADS / 32) {
-        const uint32_t grow = key_row(sb[i]);
-        const size_t local = (size_t)(grow - (uint32_t)p.row_base);
-        float d = 0.0f, xx = 0.0f;
-        // fp32 rows, dim % 4 == 0, 16-byte aligned (tc_common_ok): 128-bit loads, all of a row's requests in flight
-        const float4 *x4 = reinterpret_cast<const float4 *>(static_cast<const float *>(p.rows) + local * p.dim);
-        const float4 *q4 = reinterpret_cast<const float4 *>(qs);
-#pragma unroll 8
-        for (uint32_t j = lane; j < p.dim / 4; j += 32) {
-            const float4 v = __ldg(x4 + j), u = q4[j];
-            if (p.metric == NK_METRIC_EUCLIDEAN) {
-                float t;
-                t = v.x - u.x; d = fmaf(t, t, d);
-                t = v.y - u.y; d = fmaf(t, t, d);
-                t = v.z - u.z; d = fmaf(t, t, d);
-                t = v.w - u.w; d = fmaf(t, t, d);
-            } else {
-                d = fmaf(v.x, u.x, d); xx = fmaf(v.x, v.x, xx);
-                d = fmaf(v.y, u.y, d); xx = fmaf(v.y, v.y, xx);
-                d = fmaf(v.z, u.z, d); xx = fmaf(v.z, v.z, xx);
-                d = fmaf(v.w, u.w, d); xx = fmaf(v.w, v.w, xx);
-            }
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            d += __shfl_xor_sync(0xffffffffu, d, o);
-            xx += __shfl_xor_sync(0xffffffffu, xx, o);
-        }
-        if (lane == 0) {
-            float sc = d;
-            if (p.metric == NK_METRIC_EUCLIDEAN) sc = -d;
-            else if (p.metric == NK_METRIC_COSINE) {
-                float den = sqrtf(xx * s_qq);
-                sc = den > 0.0f ? d / den : 0.0f;
-            }
-            if (sc != sc) sc = -INFINITY;
-            se[i] = make_key(sc, grow);
-        }
-    }
-    int P2 = 32;
-    while (P2 < count) P2 <<= 1;
-    for (int i = count + tid; i < P2; i += FINISH_THREADS) se[i] = 0ull;
-    block_bitonic_sort_desc(se, P2);
-    for (uint32_t i = tid; i < p.k; i += FINISH_THREADS) p.out[(size_t)q * p.k + i] = (int)i < count ? se[i] : 0ull;
-}
-
-// Staged fallback (all on the device, no host round trip):  BF16 filter -> TF32 filter -> exact.  After a stage,
-// retry_mark moves its overflow flag [1] to the retry marker [5] and clears [1]; retry_zero wipes the shared thresholds
-// and list fills if a retry is due.  The next stage's kernels run only_if flags[5] != 0.
-__global__ void retry_mark_kernel(int *flags) {
-    flags[5] = flags[1] != 0;
-    flags[1] = 0;
-}
-__global__ void retry_zero_kernel(const int *only_if, unsigned long long *words, uint32_t n) {
-    if (*only_if == 0) return;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) words[i] = 0ull;
+    if (tid == 0) p.flags[FLAG_FINISH_CTAS] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -681,7 +891,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int tc_make_map(CUtensorMap *m, const void *base, uint64_t rows, uint32_t cols, uint32_t elem_bytes, uint32_t box_cols,
-                uint32_t box_rows, uint64_t row_stride_bytes) {
+                uint32_t box_rows, uint64_t row_stride_bytes, int map_dtype) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -691,7 +901,9 @@ int tc_make_map(CUtensorMap *m, const void *base, uint64_t rows, uint32_t cols, 
     cuuint64_t gstride[1] = {(cuuint64_t)row_stride_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+    const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                   : map_dtype == NK_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUresult r = enc(m, dt, 2,
                      const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -700,13 +912,51 @@ int tc_make_map(CUtensorMap *m, const void *base, uint64_t rows, uint32_t cols, 
     }
     return 0;
 }
-static int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint32_t dim, uint32_t box_rows) {
-    return tc_make_map(m, base, rows, dim, 4, (uint32_t)tc::BK, box_rows, (uint64_t)dim * 4);
+// Tensor maps are cached per shard: cuTensorMapEncodeTiled (1-2 us of host time each, three per launch) runs only when
+// the base pointer or the shape changed since the previous search.
+const CUtensorMap *tc_cached_map(Workspace &ws, int slot, const void *base, uint64_t rows, uint32_t cols, uint32_t elem_bytes,
+                                 uint32_t box_cols, uint32_t box_rows, uint64_t row_stride_bytes, int map_dtype) {
+    static_assert(sizeof(CUtensorMap) == sizeof(ws.maps[0].bytes), "CUtensorMap is 128 bytes");
+    Workspace::MapSlot &m = ws.maps[slot];
+    const uint64_t key[6] = {reinterpret_cast<uint64_t>(base), rows, ((uint64_t)cols << 32) | elem_bytes,
+                             ((uint64_t)box_cols << 32) | box_rows, row_stride_bytes, (uint64_t)map_dtype};
+    if (!m.valid || memcmp(m.key, key, sizeof(key)) != 0) {
+        if (tc_make_map(reinterpret_cast<CUtensorMap *>(m.bytes), base, rows, cols, elem_bytes, box_cols, box_rows, row_stride_bytes, map_dtype))
+            return nullptr;
+        memcpy(m.key, key, sizeof(key));
+        m.valid = true;
+    }
+    return reinterpret_cast<const CUtensorMap *>(m.bytes);
+}
+
+// getenv once per variable (the search path used to call getenv per search)
+int tc_env_int(const char *name, int dflt) {
+    static std::mutex mu;
+    static std::map<std::string, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(name);
+    if (it != cache.end()) return it->second;
+    const char *e = getenv(name);
+    const int v = e ? atoi(e) : dflt;
+    cache[name] = v;
+    return v;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of once per launch
+int tc_ensure_smem(const void *func, int device, size_t smem) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> done;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t &cur = done[{func, device}];
+    if (cur >= smem && cur != 0) return 0;
+    NK_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cur = smem;
+    return 0;
 }
 
 static bool tc_common_ok(const DeviceInfo &di, const ScanArgs &a) {
     if (di.cc < 100) return false;
-    if (a.dtype != NK_DTYPE_F32) return false;                      // fp16 corpus: CUDA-core scan (HBM-bound at small Q)
+    if (a.dtype != NK_DTYPE_F32) return false;                      // fp16 / bf16 corpus: 16-bit tensor pass or CUDA cores
     if (a.dim % 4 != 0 || a.dim < 32) return false;                 // TMA: 16-byte global stride
     if ((reinterpret_cast<uintptr_t>(a.rows) & 15) != 0) return false;
     if (a.n == 0 || a.k == 0) return false;
@@ -716,42 +966,52 @@ static bool tc_common_ok(const DeviceInfo &di, const ScanArgs &a) {
 bool scan_tensor_supported(const DeviceInfo &di, const ScanArgs &a) {
     return tc_common_ok(di, a) && a.metric != NK_METRIC_EUCLIDEAN && a.k + tc::ROWS + 1 <= (uint32_t)tc::P;
 }
-// filter (1xTF32 + exact rescoring) mode: all three metrics, k <= 192
+// filter mode (1xTF32 over fp32 rows, or the 16-bit pass over a shadow / a 16-bit corpus) + exact rescoring: all three
+// metrics, k <= 192
 bool scan_tensor_filter_supported(const DeviceInfo &di, const ScanArgs &a) {
-    return tc_common_ok(di, a) && a.k <= 192 && a.dim <= 32768;  // finish kernel keeps the query in shared memory
+    if (a.k > 192 || a.dim > 32768) return false;  // finish kernel keeps the query in shared memory
+    return tc_common_ok(di, a) || shadow_pass_supported(di, a);
 }
 
-int tc_debug_flags() {
-    const char *dbg = getenv("NK_TC_DEBUG");
-    return dbg ? atoi(dbg) : 0;
-}
+int tc_debug_flags() { return tc_env_int("NK_TC_DEBUG", 0); }
 
 // One launch: queries [q0, q0+nq) against the whole shard, QT = 64 or 128 query columns per MMA.
-template <int NT, int QT>
-static int launch_pass(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint32_t grid, uint32_t k_emit, float margin_c,
-                       const float *qhi, const float *qlo, const float *qnorm, uint32_t Qpad, uint32_t q0, uint32_t nq,
-                       const int *only_if, uint64_t *launches, bool count_main, uint32_t qgroups = 1) {
+struct TcPassArgs {
+    uint32_t grid, k_emit, Qpad, q0, nq, qgroups;
+    float margin_c;
+    const float *qhi, *qlo, *qnorm;
+    const int *only_if;
+    bool count_main;
+    int presampled;
+    float *dump_est = nullptr, *dump_bnd = nullptr;
+    uint32_t dump_ld = 0;
+};
+template <int NT, int QT, bool DUMP = false>
+static int launch_pass(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, const TcPassArgs &t, uint64_t *launches) {
     using namespace tc;
-    CUtensorMap map_rows, map_qhi, map_qlo;
-    if (make_map(&map_rows, a.rows, a.n, a.dim, ROWS)) return -1;
-    if (make_map(&map_qhi, qhi, Qpad, a.dim, QT)) return -1;          // rows past Qpad are zero-filled by TMA
-    if (make_map(&map_qlo, qlo ? qlo : qhi, Qpad, a.dim, QT)) return -1;
+    const CUtensorMap *map_rows = tc_cached_map(ws, 0, a.rows, a.n, a.dim, 4, (uint32_t)BK, ROWS, (uint64_t)a.dim * 4);
+    // query rows past Qpad are zero-filled by TMA
+    const CUtensorMap *map_qhi = tc_cached_map(ws, QT == 64 ? 1 : 2, t.qhi, t.Qpad, a.dim, 4, (uint32_t)BK, QT, (uint64_t)a.dim * 4);
+    const CUtensorMap *map_qlo = NT == 3 ? tc_cached_map(ws, 3, t.qlo, t.Qpad, a.dim, 4, (uint32_t)BK, QT, (uint64_t)a.dim * 4) : map_qhi;
+    if (!map_rows || !map_qhi || !map_qlo) return -1;
     const size_t smem = (size_t)Cfg<NT, QT>::RING_BYTES + sizeof(Shared) + 1024;
     if (smem > di.max_smem_optin) {
         set_error("tensor path needs %zu B shared memory (> %zu)", smem, di.max_smem_optin);
         return -1;
     }
-    NK_CUDA_OK(cudaFuncSetAttribute(knn_scan_tc_kernel<NT, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    Params p;
+    if (tc_ensure_smem(reinterpret_cast<const void *>(knn_scan_tc_kernel<NT, QT, DUMP>), di.device_id, smem)) return -1;
+    Params p{};
     p.n = a.n; p.dim = a.dim; p.nslab = (a.dim + BK - 1) / BK; p.row_base = a.row_base;
-    p.q0 = q0; p.nq = nq; p.k = a.k; p.qpad_off = q0; p.qgroups = qgroups; p.list_cap = grid * k_emit;
-    p.metric = a.metric; p.k_emit = k_emit; p.margin_c = margin_c; p.qnorm = qnorm;
-    p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = only_if; p.debug = tc_debug_flags(); p.mask = a.row_mask;
-    p.gtau = reinterpret_cast<uint32_t *>(ws.keys2); p.gcount = reinterpret_cast<int *>(ws.keys2) + (Qpad + QT_BIG);
-    knn_scan_tc_kernel<NT, QT><<<grid, THREADS, smem, a.stream>>>(map_rows, map_qhi, map_qlo, p);
+    p.q0 = t.q0; p.nq = t.nq; p.k = a.k; p.qpad_off = t.q0; p.qgroups = t.qgroups; p.list_cap = t.grid * t.k_emit;
+    p.metric = a.metric; p.k_emit = t.k_emit; p.margin_c = t.margin_c; p.qnorm = t.qnorm;
+    p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = t.only_if; p.debug = tc_debug_flags(); p.mask = a.row_mask;
+    p.gtau = reinterpret_cast<uint32_t *>(ws.keys2); p.gcount = reinterpret_cast<int *>(ws.keys2) + (t.Qpad + QT_BIG);
+    p.presampled = t.presampled; p.min_score = a.min_score;
+    p.dump_est = t.dump_est; p.dump_bnd = t.dump_bnd; p.dump_ld = t.dump_ld;
+    knn_scan_tc_kernel<NT, QT, DUMP><<<t.grid, THREADS, smem, a.stream>>>(*map_rows, *map_qhi, *map_qlo, p);
     NK_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
-    if (count_main && a.main_launches) ++*a.main_launches;
+    if (t.count_main && a.main_launches) ++*a.main_launches;
     return 0;
 }
 
@@ -768,7 +1028,74 @@ static void tc_print_prof(cudaStream_t stream, uint32_t num_tiles, uint32_t grid
             slabs, h[7], (double)h[7] / slabs, h[0], h[2], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15], h[16], h[17], h[18]);
 }
 
+// ---- the plan of one filter search: everything both the primary stage and the (possibly deferred) tail derive from
+// (device, args).  Deterministic, so the host-driven retry of nk_search can rebuild it after the fact.
+struct FilterPlan {
+    uint32_t Qpad, QA, num_tiles, grid, k_emit, dimpad, sample;
+    bool big;           // first stage = 16-bit pass (BF16 shadow of an fp32 shard, or an fp16 / bf16 corpus itself)
+    bool stage2;        // the TF32 filter over the fp32 rows exists as the retry stage (fp32 shards with a shadow)
+    bool can_exact_tc;  // exact stage = 3xTF32 kernel (else the CUDA-core scan)
+    float acc_c, margin_tf32;
+    float *qhi, *qlo, *qnorm, *qa, *qb;
+    void *qbf16;
+    uint32_t max_groups, max_groups_shadow;
+    size_t fsmem, psmem;
+};
+
+static int make_filter_plan(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, FilterPlan *fp) {
+    using namespace tc;
+    FilterPlan &f = *fp;
+    f.Qpad = (a.Q + 63) / 64 * 64;
+    f.QA = f.Qpad + QT_BIG;  // padded per-query arrays
+    f.num_tiles = (a.n + ROWS - 1) / ROWS;
+    f.grid = (uint32_t)di.num_sms < f.num_tiles ? (uint32_t)di.num_sms : f.num_tiles;
+    // per-CTA contribution: at most k + room for the rows inside the margin
+    f.k_emit = next_pow2(a.k + a.k / 2 + 32);
+    if (f.k_emit < 64) f.k_emit = 64;
+    if (f.k_emit > (uint32_t)(P - ROWS)) f.k_emit = P - ROWS;
+    // TF32: 2^-10 (rounding of both operands, unit roundoff 2^-11 each) + d * 2^-22 (fp32 accumulation, truncating
+    // adders) + fp32 rounding of the norms.  The 16-bit kernel measures its rounding residues instead.
+    f.acc_c = (float)a.dim * 2.384185791015625e-7f + 4e-6f;
+    f.margin_tf32 = 9.765625e-4f + f.acc_c;
+    f.big = shadow_pass_supported(di, a);
+    f.stage2 = f.big && a.dtype == NK_DTYPE_F32 && tc_common_ok(di, a);
+    f.can_exact_tc = scan_tensor_supported(di, a);  // euclidean / 16-bit rows have no 3xTF32 twin: overflow -> CUDA-core scan
+    if (f.big && f.k_emit < 128) f.k_emit = 128;  // BF16 margins are ~3x wider: more rows per CTA sit inside them
+    f.dimpad = f.big ? a.shadow_dimpad : (a.dim + 63) / 64 * 64;
+    const bool need_f32q = a.dtype == NK_DTYPE_F32;  // hi / lo arrays only serve passes over fp32 rows
+    const size_t qaux_floats = (need_f32q ? (size_t)2 * f.Qpad * a.dim : 0) + (size_t)3 * f.QA;
+    if (ws_reserve((void **)&ws.qaux, &ws.qaux_bytes, qaux_floats * 4 + (f.big ? (size_t)f.Qpad * f.dimpad * 2 : 0))) return -1;
+    if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)f.grid * QT_MAX * P * 8)) return -1;
+    if (ws_reserve((void **)&ws.partial, &ws.partial_bytes, (size_t)a.Q * f.grid * f.k_emit * 8)) return -1;
+    if (ws_reserve((void **)&ws.keys2, &ws.keys2_bytes, (size_t)f.QA * 8)) return -1;  // gtau[] + gcount[]
+    f.qhi = need_f32q ? ws.qaux : nullptr;
+    f.qlo = need_f32q ? ws.qaux + (size_t)f.Qpad * a.dim : nullptr;
+    f.qnorm = ws.qaux + (need_f32q ? (size_t)2 * f.Qpad * a.dim : 0);
+    f.qa = f.qnorm + f.QA;
+    f.qb = f.qa + f.QA;
+    f.qbf16 = ws.qaux + qaux_floats;
+    f.max_groups = (uint32_t)tc_env_int("NK_TC_QGROUPS", 4);
+    // G query groups leave each CTA 1/G of the grid for its queries, i.e. G times the rows — and G times the rows inside
+    // the BF16 margin — per (CTA, query) buffer: large k keeps fewer groups so that k + margin rows stay inside k_emit
+    f.max_groups_shadow = a.k <= 32 ? 4u : a.k <= 64 ? 2u : 1u;
+    if (f.max_groups_shadow > f.max_groups) f.max_groups_shadow = f.max_groups;
+    // Sampled initial threshold: single-pass batches on shards with enough tiles per CTA for the flood tiles to matter.
+    // (Large batches re-score the sample once per query — more L2 traffic than the flood tiles cost.)
+    f.sample = 0;
+    if (tc_env_int("NK_TAU_SAMPLE", 1) && a.Q <= 128 && a.n >= 4096) {
+        f.sample = next_pow2(16 * a.k);
+        if (f.sample < 256) f.sample = 256;
+        if (f.sample > 2048) f.sample = 2048;
+    }
+    f.fsmem = (size_t)FINISH_CAP * 16 + (size_t)a.dim * 4;
+    f.psmem = (size_t)((a.dim + 3) & ~3u) * 4 + (size_t)f.sample * 8;
+    if (tc_ensure_smem(reinterpret_cast<const void *>(filter_finish_kernel), di.device_id, f.fsmem)) return -1;
+    if (f.psmem > 48 * 1024 && tc_ensure_smem(reinterpret_cast<const void *>(filter_prep_kernel), di.device_id, f.psmem)) return -1;
+    return 0;
+}
+
 // Exact 3xTF32 scan.  only_if != nullptr: every kernel early-exits unless *only_if != 0 (device-side fallback).
+// prep: convert the queries here (stand-alone use); the filter path has already done it in its fused prep.
 static int scan_tensor_exact(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *out_keys, uint64_t *launches,
                              const int *only_if, bool prep, bool count_main) {
     using namespace tc;
@@ -779,16 +1106,23 @@ static int scan_tensor_exact(const DeviceInfo &di, const ScanArgs &a, Workspace 
     if (ws_reserve((void **)&ws.qaux, &ws.qaux_bytes, ((size_t)2 * Qpad * a.dim + Qpad + QT_MAX) * 4)) return -1;
     if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)grid * QT_MAX * P * 8)) return -1;
     if (ws_reserve((void **)&ws.partial, &ws.partial_bytes, (size_t)a.Q * grid * a.k * 8)) return -1;
-    float *qhi = ws.qaux, *qlo = ws.qaux + (size_t)Qpad * a.dim, *qnorm = ws.qaux + (size_t)2 * Qpad * a.dim;
+    float *qhi = ws.qaux, *qlo = ws.qaux + (size_t)Qpad * a.dim;
     if (prep) {
-        tc_prep_queries_kernel<<<Qpad, 256, 0, a.stream>>>(a.queries, a.Q, a.dim, a.metric == NK_METRIC_COSINE, qhi, qlo, qnorm);
+        PrepParams pp{};
+        pp.q = a.queries; pp.Q = a.Q; pp.dim = a.dim; pp.dimpad = a.dim; pp.normalise = a.metric == NK_METRIC_COSINE; pp.metric = a.metric;
+        pp.qhi = qhi; pp.qlo = qlo; pp.Qpad = Qpad; pp.only_if = only_if;
+        const size_t psmem = (size_t)((a.dim + 3) & ~3u) * 4;
+        if (psmem > 48 * 1024 && tc_ensure_smem(reinterpret_cast<const void *>(filter_prep_kernel), di.device_id, psmem)) return -1;
+        filter_prep_kernel<<<Qpad, PREP_THREADS, psmem, a.stream>>>(pp);
         NK_CUDA_OK(cudaGetLastError());
         if (launches) ++*launches;
     }
     if (count_main && a.ev_begin) NK_CUDA_OK(cudaEventRecord(a.ev_begin, a.stream));
     for (uint32_t q0 = 0; q0 < a.Q; q0 += 64) {
-        const uint32_t nq = a.Q - q0 < 64u ? a.Q - q0 : 64u;
-        if (launch_pass<3, 64>(di, a, ws, grid, a.k, 0.0f, qhi, qlo, nullptr, Qpad, q0, nq, only_if, launches, count_main)) return -1;
+        TcPassArgs t{};
+        t.grid = grid; t.k_emit = a.k; t.Qpad = Qpad; t.q0 = q0; t.nq = a.Q - q0 < 64u ? a.Q - q0 : 64u; t.qgroups = 1;
+        t.qhi = qhi; t.qlo = qlo; t.only_if = only_if; t.count_main = count_main;
+        if (launch_pass<3, 64>(di, a, ws, t, launches)) return -1;
     }
     if (count_main && a.ev_end) NK_CUDA_OK(cudaEventRecord(a.ev_end, a.stream));
     if (merge_keys(ws.partial, grid, a.k, (size_t)grid * a.k, a.Q, a.k, out_keys, a.stream, only_if)) return -1;
@@ -803,11 +1137,83 @@ int scan_tensor(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t
         set_error("tensor path: unsupported shape");
         return -1;
     }
-    return scan_tensor_exact(di, a, ws, out_keys, launches, nullptr, true, true);
+    if (scan_tensor_exact(di, a, ws, out_keys, launches, nullptr, true, true)) return -1;
+    if (a.out_idx && decode_keys(out_keys, a.Q, a.k, a.metric, a.out_idx, a.out_score, a.stream)) return -1;
+    if (a.out_idx && launches) ++*launches;
+    return 0;
 }
 
-// Filter mode: 1xTF32 scan with rigorous margins -> merge by upper bound -> exact fp32 rescoring; the exact 3xTF32
-// search is enqueued behind it and runs only if the device-side overflow flag was raised.
+// TF32 passes over queries [qfirst, Q): 128 query columns per MMA while more than 64 queries remain (twice the queries per
+// corpus byte streamed), a 64-column launch for the tail; 2 or 4 query blocks per launch share every corpus tile through
+// L2 (sibling CTAs).
+static int tf32_passes(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, const FilterPlan &f, uint32_t qfirst, const int *only_if,
+                       bool count_main, int presampled, uint64_t *launches) {
+    for (uint32_t q0 = qfirst; q0 < a.Q;) {
+        const uint32_t left = a.Q - q0;
+        TcPassArgs t{};
+        t.grid = f.grid; t.k_emit = f.k_emit; t.Qpad = f.Qpad; t.q0 = q0; t.margin_c = f.margin_tf32;
+        t.qhi = f.qhi; t.qnorm = f.qnorm; t.only_if = only_if; t.count_main = count_main; t.presampled = presampled;
+        if (left > 64) {
+            uint32_t groups = 1;
+            if (left > 3 * 128 && f.max_groups >= 4 && f.grid % 4 == 0 && f.grid >= 8) groups = 4;
+            else if (left > 128 && f.max_groups >= 2 && f.grid % 2 == 0 && f.grid >= 4) groups = 2;
+            t.nq = left < 128u * groups ? left : 128u * groups;
+            t.qgroups = groups;
+            if (launch_pass<1, 128>(di, a, ws, t, launches)) return -1;
+        } else {
+            t.nq = left; t.qgroups = 1;
+            if (launch_pass<1, 64>(di, a, ws, t, launches)) return -1;
+        }
+        q0 += t.nq;
+    }
+    return 0;
+}
+
+static void fill_finish(FinishParams &fp, const ScanArgs &a, Workspace &ws, const FilterPlan &f, uint64_t *out_keys) {
+    fp.rows = a.rows; fp.dtype = a.dtype; fp.dim = a.dim; fp.row_base = a.row_base; fp.queries = a.queries;
+    fp.lists = ws.partial; fp.gcount = reinterpret_cast<const int *>(ws.keys2) + f.QA; fp.list_cap = f.grid * f.k_emit; fp.k = a.k;
+    fp.metric = a.metric; fp.margin_c = f.margin_tf32; fp.flags = ws.flags; fp.out = out_keys;
+    fp.out_idx = a.out_idx; fp.out_score = a.out_score; fp.min_score = a.min_score;
+    fp.qa = f.qa; fp.qb = f.qb; fp.qn = f.qnorm;
+    fp.state = reinterpret_cast<uint32_t *>(ws.keys2); fp.state_words = 2 * f.QA;
+}
+
+// The retry / exact stages of a filter search.  Every kernel returns at once unless the stage before raised its flag on
+// the device, so the tail can be queued blindly behind the first stage (asynchronous API: no host round trip) — or, for
+// the host-synchronous API, only after the host has seen a flag (a_defer_tail): the common case then launches nothing.
+int scan_tensor_filter_tail(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *out_keys, uint64_t *launches) {
+    using namespace tc;
+    FilterPlan f;
+    if (make_filter_plan(di, a, ws, &f)) return -1;
+    if (f.stage2) {
+        // the same search over the fp32 rows with the (much tighter) TF32 margins, if a 16-bit margin buffer overflowed
+        if (tf32_passes(di, a, ws, f, 0, ws.flags + FLAG_RETRY, false, 0, launches)) return -1;
+        FinishParams fp{};
+        fill_finish(fp, a, ws, f, out_keys);
+        fp.q_big = 0; fp.only_if = ws.flags + FLAG_RETRY; fp.mark_retry = 0;
+        filter_finish_kernel<<<a.Q, FINISH_THREADS, f.fsmem, a.stream>>>(fp);
+        NK_CUDA_OK(cudaGetLastError());
+        if (launches) ++*launches;
+    }
+    ScanArgs b = a;
+    b.ev_begin = b.ev_end = nullptr;
+    b.main_launches = nullptr;
+    if (f.can_exact_tc) {
+        if (scan_tensor_exact(di, b, ws, out_keys, launches, ws.flags + FLAG_OVERFLOW, false, false)) return -1;
+    } else {  // euclidean / large k / 16-bit rows: the CUDA-core scan is the exact twin
+        b.only_if = ws.flags + FLAG_OVERFLOW;
+        b.out_idx = nullptr; b.out_score = nullptr;
+        if (scan_simt(di, b, ws, out_keys, launches)) return -1;
+    }
+    if (a.out_idx) {
+        if (decode_keys(out_keys, a.Q, a.k, a.metric, a.out_idx, a.out_score, a.stream, ws.flags + FLAG_OVERFLOW)) return -1;
+        if (launches) ++*launches;
+    }
+    return 0;
+}
+
+// Filter mode: prep -> 16-bit (or 1xTF32) scan with rigorous margins -> finish (select by upper bound, exact fp32
+// rescoring, decode).  Three launches in the common case; the retry / exact stages follow as scan_tensor_filter_tail.
 int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *out_keys, uint64_t *launches) {
     using namespace tc;
     if (a.n == 0 || a.Q == 0 || a.k == 0) return 0;
@@ -815,123 +1221,91 @@ int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
         set_error("tensor filter path: unsupported shape");
         return -1;
     }
-    const uint32_t Qpad = (a.Q + 63) / 64 * 64;
-    const uint32_t num_tiles = (a.n + ROWS - 1) / ROWS;
-    uint32_t grid = (uint32_t)di.num_sms;
-    if (grid > num_tiles) grid = num_tiles;
-    // per-CTA contribution: at most k + room for the rows inside the margin
-    uint32_t k_emit = next_pow2(a.k + a.k / 2 + 32);
-    if (k_emit < 64) k_emit = 64;
-    if (k_emit > (uint32_t)(P - ROWS)) k_emit = P - ROWS;
-    // TF32: 2^-10 (rounding of both operands, unit roundoff 2^-11 each) + d * 2^-22 (fp32 accumulation, truncating
-    // adders) + fp32 rounding of the norms.  The BF16 kernel (big batches) measures its rounding residues instead.
-    const float acc_c = (float)a.dim * 2.384185791015625e-7f + 4e-6f;
-    const float margin_tf32 = 9.765625e-4f + acc_c;
-    // a BF16 shadow of the shard (scan_tensor_shadow.cu) halves the bytes the filter streams; the TF32 scan over the fp32
-    // rows is then the retry stage
-    const bool big = shadow_pass_supported(di, a);
-    if (big && k_emit < 128) k_emit = 128;  // BF16 margins are ~3x wider: more rows per CTA sit inside them
-    const uint32_t dimpad = big ? a.shadow_dimpad : (a.dim + 63) / 64 * 64;
-    const uint32_t QA = Qpad + QT_BIG;  // padded per-query arrays
+    FilterPlan f;
+    if (make_filter_plan(di, a, ws, &f)) return -1;
+    const uint32_t q_big = f.big ? a.Q : 0;  // queries served by the 16-bit kernel in the first stage (all or none)
 
-    const size_t qaux_floats = (size_t)2 * Qpad * a.dim + (size_t)3 * QA;
-    if (ws_reserve((void **)&ws.qaux, &ws.qaux_bytes, qaux_floats * 4 + (big ? (size_t)Qpad * dimpad * 2 : 0))) return -1;
-    if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)grid * QT_MAX * P * 8)) return -1;
-    if (ws_reserve((void **)&ws.partial, &ws.partial_bytes, (size_t)a.Q * grid * k_emit * 8)) return -1;
-    if (ws_reserve((void **)&ws.keys2, &ws.keys2_bytes, (size_t)QA * 8)) return -1;  // gtau[] + gcount[]
-    float *qhi = ws.qaux, *qlo = ws.qaux + (size_t)Qpad * a.dim, *qnorm = ws.qaux + (size_t)2 * Qpad * a.dim;
-    float *qa = qnorm + QA, *qb = qa + QA;
-    void *qbf16 = ws.qaux + qaux_floats;
-
-    NK_CUDA_OK(cudaMemsetAsync(ws.flags + 1, 0, 7 * sizeof(int), a.stream));  // overflow, running maxima, retry marker
-    NK_CUDA_OK(cudaMemsetAsync(ws.keys2, 0, (size_t)QA * 8, a.stream));        // shared thresholds + list fills
-    const bool can_fallback = scan_tensor_supported(di, a);  // euclidean has no 3xTF32 twin: overflow -> CUDA-core scan
-    uint32_t max_groups = 4;
-    if (const char *e = getenv("NK_TC_QGROUPS")) max_groups = (uint32_t)atoi(e);
-    // G query groups leave each CTA 1/G of the grid for its queries, i.e. G times the rows — and G times the rows inside
-    // the BF16 margin — per (CTA, query) buffer: large k keeps fewer groups so that k + margin rows stay inside k_emit
-    uint32_t max_groups_shadow = a.k <= 32 ? 4u : a.k <= 64 ? 2u : 1u;
-    if (max_groups_shadow > max_groups) max_groups_shadow = max_groups;
-    const uint32_t q_big = big ? a.Q : 0;  // queries served by the shadow kernel in the first stage (all or none)
-    tc_prep_queries_kernel<<<Qpad, 256, 0, a.stream>>>(a.queries, a.Q, a.dim, a.metric == NK_METRIC_COSINE, qhi,
-                                                       can_fallback ? qlo : nullptr, qnorm);
+    PrepParams pp{};
+    pp.q = a.queries; pp.Q = a.Q; pp.dim = a.dim; pp.dimpad = f.dimpad; pp.normalise = a.metric == NK_METRIC_COSINE; pp.metric = a.metric;
+    pp.acc_c = f.acc_c;
+    pp.qhi = f.qhi; pp.qlo = f.can_exact_tc ? f.qlo : nullptr;
+    pp.qbf = f.big ? static_cast<uint16_t *>(f.qbf16) : nullptr; pp.qbf_f16 = a.dtype == NK_DTYPE_F16;
+    pp.qnorm = f.qnorm; pp.qa = f.qa; pp.qb = f.qb;
+    pp.state = reinterpret_cast<uint32_t *>(ws.keys2); pp.Qpad = f.Qpad; pp.QA = f.QA; pp.flags = ws.flags;
+    pp.rows = a.rows; pp.dtype = a.dtype; pp.n = a.n; pp.sample = f.sample; pp.k = a.k; pp.mask = a.row_mask; pp.min_score = a.min_score;
+    filter_prep_kernel<<<f.Qpad, PREP_THREADS, f.psmem, a.stream>>>(pp);
     NK_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
-    if (q_big && bf16_prep_queries(a, Qpad, dimpad, acc_c, qbf16, qnorm, qa, qb, launches)) return -1;
-
-    FinishParams fp;
-    fp.rows = a.rows; fp.dim = a.dim; fp.row_base = a.row_base; fp.queries = a.queries;
-    fp.lists = ws.partial; fp.gcount = reinterpret_cast<const int *>(ws.keys2) + QA; fp.list_cap = grid * k_emit; fp.k = a.k;
-    fp.metric = a.metric; fp.margin_c = margin_tf32; fp.flags = ws.flags; fp.out = out_keys;
-    fp.qa = qa; fp.qb = qb; fp.qn = qnorm;
-    const size_t fsmem = (size_t)FINISH_CAP * 16 + (size_t)a.dim * 4;
-    NK_CUDA_OK(cudaFuncSetAttribute(filter_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-
-    // TF32 passes over queries [qfirst, Q): 128 query columns per MMA while more than 64 queries remain (twice the queries
-    // per corpus byte streamed), a 64-column launch for the tail; 2 or 4 query blocks per launch share every corpus tile
-    // through L2 (sibling CTAs).
-    auto tf32_passes = [&](uint32_t qfirst, const int *only_if, bool count_main) -> int {
-        for (uint32_t q0 = qfirst; q0 < a.Q;) {
-            const uint32_t left = a.Q - q0;
-            if (left > 64) {
-                uint32_t groups = 1;
-                if (left > 3 * 128 && max_groups >= 4 && grid % 4 == 0 && grid >= 8) groups = 4;
-                else if (left > 128 && max_groups >= 2 && grid % 2 == 0 && grid >= 4) groups = 2;
-                const uint32_t nq = left < 128u * groups ? left : 128u * groups;
-                if (launch_pass<1, 128>(di, a, ws, grid, k_emit, margin_tf32, qhi, nullptr, qnorm, Qpad, q0, nq, only_if, launches, count_main, groups)) return -1;
-                q0 += nq;
-            } else {
-                if (launch_pass<1, 64>(di, a, ws, grid, k_emit, margin_tf32, qhi, nullptr, qnorm, Qpad, q0, left, only_if, launches, count_main)) return -1;
-                q0 += left;
-            }
-        }
-        return 0;
-    };
 
     if (a.ev_begin) NK_CUDA_OK(cudaEventRecord(a.ev_begin, a.stream));
-    for (uint32_t q0 = 0; q0 < q_big;) {  // shadow passes: 128 query columns (up to 4 query groups per launch), 64 for the tail
+    for (uint32_t q0 = 0; q0 < q_big;) {  // 16-bit passes: 128 query columns (up to 4 query groups per launch), 64 for the tail
         const uint32_t left = q_big - q0;
+        ShadowPassArgs sp{};
+        sp.grid = f.grid; sp.k_emit = f.k_emit; sp.dimpad = f.dimpad; sp.Qpad = f.Qpad; sp.q0 = q0;
+        sp.qbf16 = f.qbf16; sp.qnorm = f.qnorm; sp.qa = f.qa; sp.qb = f.qb; sp.presampled = f.sample != 0;
         if (left > 64) {
             uint32_t groups = 1;
-            if (left > 3 * 128 && max_groups_shadow >= 4 && grid % 4 == 0 && grid >= 8) groups = 4;
-            else if (left > 128 && max_groups_shadow >= 2 && grid % 2 == 0 && grid >= 4) groups = 2;
-            const uint32_t nq = left < 128u * groups ? left : 128u * groups;
-            if (launch_shadow_pass(128, di, a, ws, grid, k_emit, qbf16, dimpad, qnorm, qa, qb, Qpad, q0, nq, groups, launches)) return -1;
-            q0 += nq;
+            if (left > 3 * 128 && f.max_groups_shadow >= 4 && f.grid % 4 == 0 && f.grid >= 8) groups = 4;
+            else if (left > 128 && f.max_groups_shadow >= 2 && f.grid % 2 == 0 && f.grid >= 4) groups = 2;
+            sp.nq = left < 128u * groups ? left : 128u * groups;
+            sp.qgroups = groups;
+            if (launch_shadow_pass(128, di, a, ws, sp, launches)) return -1;
         } else {
-            if (launch_shadow_pass(64, di, a, ws, grid, k_emit, qbf16, dimpad, qnorm, qa, qb, Qpad, q0, left, 1, launches)) return -1;
-            q0 += left;
+            sp.nq = left; sp.qgroups = 1;
+            if (launch_shadow_pass(64, di, a, ws, sp, launches)) return -1;
         }
+        q0 += sp.nq;
     }
-    if (tf32_passes(q_big, nullptr, true)) return -1;
+    if (!f.big && tf32_passes(di, a, ws, f, 0, nullptr, true, f.sample != 0, launches)) return -1;
     if (a.ev_end) NK_CUDA_OK(cudaEventRecord(a.ev_end, a.stream));
-    fp.q_big = q_big; fp.only_if = nullptr;
-    filter_finish_kernel<<<a.Q, FINISH_THREADS, fsmem, a.stream>>>(fp);
+
+    FinishParams fp{};
+    fill_finish(fp, a, ws, f, out_keys);
+    fp.q_big = q_big; fp.only_if = nullptr; fp.mark_retry = f.stage2 ? 1 : 0;
+    filter_finish_kernel<<<a.Q, FINISH_THREADS, f.fsmem, a.stream>>>(fp);
     NK_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
-    if (q_big) {
-        // retry stage, queued behind and skipped on the device unless a BF16 margin buffer overflowed: the same search over
-        // the fp32 rows with the (much tighter) TF32 margins
-        retry_mark_kernel<<<1, 1, 0, a.stream>>>(ws.flags);
-        retry_zero_kernel<<<(QA + 255) / 256, 256, 0, a.stream>>>(ws.flags + 5, reinterpret_cast<unsigned long long *>(ws.keys2), QA);
-        NK_CUDA_OK(cudaGetLastError());
-        if (launches) *launches += 2;
-        if (tf32_passes(0, ws.flags + 5, false)) return -1;
-        fp.q_big = 0; fp.only_if = ws.flags + 5;
-        filter_finish_kernel<<<a.Q, FINISH_THREADS, fsmem, a.stream>>>(fp);
-        NK_CUDA_OK(cudaGetLastError());
-        if (launches) ++*launches;
-    }
-    tc_print_prof(a.stream, num_tiles, grid, (a.dim + BK - 1) / BK);
-    // queued behind; every kernel returns at once unless flags[1] was raised on the device
-    if (can_fallback) {
-        if (scan_tensor_exact(di, a, ws, out_keys, launches, ws.flags + 1, false, false)) return -1;
+    tc_print_prof(a.stream, f.num_tiles, f.grid, (a.dim + BK - 1) / BK);
+    if (a.defer_tail) return 0;
+    return scan_tensor_filter_tail(di, a, ws, out_keys, launches);
+}
+
+// ---- tests only: the filters' raw score estimates and error bounds for every (row, query) pair --------------------
+// which: NK_PATH_TENSOR_FILTER (1xTF32 over the fp32 rows) or NK_PATH_TENSOR_SHADOW (16-bit pass).  est / bnd: device
+// [n x ld] floats.  The estimate is what the kernel compares (before adding the bound); |est - exact| <= bnd is the
+// invariant the filter's soundness rests on (tests/test_gpu_error_model.py measures it against fp64).
+int scan_filter_dump(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, int which, float *est, float *bnd, uint32_t ld,
+                     uint64_t *launches) {
+    using namespace tc;
+    if (a.Q == 0 || a.Q > 64 || a.n == 0) { set_error("dump: 1 <= Q <= 64 and n > 0 required"); return -1; }
+    ScanArgs b = a;
+    b.k = 1; b.min_score = -INFINITY; b.defer_tail = true; b.out_idx = nullptr; b.out_score = nullptr;
+    if (!scan_tensor_filter_supported(di, b)) { set_error("dump: unsupported shape"); return -1; }
+    FilterPlan f;
+    if (make_filter_plan(di, b, ws, &f)) return -1;
+    if (which == NK_PATH_TENSOR_SHADOW && !f.big) { set_error("dump: no 16-bit pass for this shard"); return -1; }
+    if (which == NK_PATH_TENSOR_FILTER && a.dtype != NK_DTYPE_F32) { set_error("dump: TF32 pass needs fp32 rows"); return -1; }
+    PrepParams pp{};
+    pp.q = b.queries; pp.Q = b.Q; pp.dim = b.dim; pp.dimpad = f.dimpad; pp.normalise = b.metric == NK_METRIC_COSINE; pp.metric = b.metric;
+    pp.acc_c = f.acc_c; pp.qhi = f.qhi; pp.qlo = nullptr;
+    pp.qbf = f.big ? static_cast<uint16_t *>(f.qbf16) : nullptr; pp.qbf_f16 = b.dtype == NK_DTYPE_F16;
+    pp.qnorm = f.qnorm; pp.qa = f.qa; pp.qb = f.qb;
+    pp.state = reinterpret_cast<uint32_t *>(ws.keys2); pp.Qpad = f.Qpad; pp.QA = f.QA; pp.flags = ws.flags;
+    pp.rows = b.rows; pp.dtype = b.dtype; pp.n = b.n; pp.sample = 0; pp.k = 1; pp.min_score = -INFINITY;
+    filter_prep_kernel<<<f.Qpad, PREP_THREADS, f.psmem, b.stream>>>(pp);
+    NK_CUDA_OK(cudaGetLastError());
+    if (launches) ++*launches;
+    if (which == NK_PATH_TENSOR_SHADOW) {
+        ShadowPassArgs sp{};
+        sp.grid = f.grid; sp.k_emit = f.k_emit; sp.dimpad = f.dimpad; sp.Qpad = f.Qpad; sp.q0 = 0; sp.nq = b.Q; sp.qgroups = 1;
+        sp.qbf16 = f.qbf16; sp.qnorm = f.qnorm; sp.qa = f.qa; sp.qb = f.qb; sp.presampled = 0;
+        sp.dump_est = est; sp.dump_bnd = bnd; sp.dump_ld = ld;
+        if (launch_shadow_pass(64, di, b, ws, sp, launches)) return -1;
     } else {
-        ScanArgs b = a;  // euclidean / large k: the CUDA-core scan is the exact twin
-        b.only_if = ws.flags + 1;
-        b.ev_begin = b.ev_end = nullptr;
-        b.main_launches = nullptr;
-        if (scan_simt(di, b, ws, out_keys, launches)) return -1;
+        TcPassArgs t{};
+        t.grid = f.grid; t.k_emit = f.k_emit; t.Qpad = f.Qpad; t.q0 = 0; t.nq = b.Q; t.qgroups = 1; t.margin_c = f.margin_tf32;
+        t.qhi = f.qhi; t.qnorm = f.qnorm; t.dump_est = est; t.dump_bnd = bnd; t.dump_ld = ld;
+        if (launch_pass<1, 64, true>(di, b, ws, t, launches)) return -1;
     }
     return 0;
 }

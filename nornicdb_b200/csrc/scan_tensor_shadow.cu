@@ -157,7 +157,7 @@ int build_shadow(const float *rows, uint64_t first, uint64_t count, uint32_t dim
     return 0;
 }
 
-template <int QT>
+template <int QT, bool DUMP>
 __global__ void __launch_bounds__(sb::NTHREADS, 1)
 knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_q, tc::Params p) {
     using namespace sb;
@@ -193,7 +193,14 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
     }
     if (warp == 2) ptx::tmem_alloc(&sh.tmem_base, TMEM_COLS);
     if (tid < QT) {
-        sh.tau[tid] = -INFINITY;
+        // start threshold: the caller's score floor and, when the prep kernel sampled the shard, a lower bound of the
+        // query's k-th best score (no flood tiles then)
+        float t0 = p.min_score;
+        if (p.presampled && (uint32_t)tid < nq) {
+            const uint32_t g = __ldcg(p.gtau + q0 + tid);
+            if (g) t0 = fmaxf(t0, ord_to_float(g));
+        }
+        sh.tau[tid] = t0;
         sh.cnt[tid] = 0;
         sh.qn[tid] = p.qnorm[qpad_off + tid];
         sh.qa[tid] = p.qa[qpad_off + tid];
@@ -203,6 +210,7 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = sh.tmem_base;
+    const bool flood = !p.presampled;  // first two tiles: every (row, query) pair is placed directly
 
     if (warp == 0) {
         // ===================================== TMA producer: shadow slabs =========================
@@ -234,7 +242,7 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =========================================
-        const uint32_t idesc = ptx::make_idesc_bf16(128, QT);
+        const uint32_t idesc = p.op_f16 ? ptx::make_idesc_f16(128, QT) : ptx::make_idesc_bf16(128, QT);
         uint32_t g = 0, it = 0;
         for (uint32_t tile = sub; tile < num_tiles; tile += sgrid, ++it) {
             const uint32_t buf = it & 1;
@@ -282,7 +290,7 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
             //   euclidean  -(|x|^2 + |q|^2 - 2 acc)        ra = 2|dx|      rb = 2|x|   (+ eps (|x|^2 + |q|^2))
             const float x2 = row < p.n ? __ldg(p.xnorm2 + row) : 0.0f;
             const float xn = sqrtf(x2);
-            const float dxn = sqrtf(row < p.n ? __ldg(p.dnorm2 + row) : 0.0f) * 1.0001f;
+            const float dxn = sqrtf((row < p.n && p.dnorm2) ? __ldg(p.dnorm2 + row) : 0.0f) * 1.0001f;  // 16-bit corpus: no residue
             float mul = 1.0f, ra = dxn, rb = xn;
             if (cosine) {
                 mul = x2 > 0.0f ? 1.0f / xn : 0.0f;
@@ -309,7 +317,23 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&sh.accempty[buf][m]);
                 }
-                if (it < 2 && cb < nq) {
+                if (DUMP && row < p.n) {  // tests only: score estimate and error bound per (row, query)
+                    for (uint32_t c = 0; c < 64 && cb + c < nq; ++c) {
+                        uint32_t bits = 0;
+#pragma unroll
+                        for (uint32_t i = 0; i < 32; ++i) {
+                            if (c == i) bits = v0[i];
+                            if (c == 32 + i) bits = v1[i];
+                        }
+                        const uint32_t qi = cb + c;
+                        const float qn = sh.qn[qi];
+                        float est = __uint_as_float(bits) * mul, b = fmaf(ra, sh.qa[qi], rb * sh.qb[qi]);
+                        if (euclid) { est -= fmaf(qn, qn, x2); b += EUC_EPS * fmaf(qn, qn, x2); }
+                        p.dump_est[(size_t)row * p.dump_ld + q0 + qi] = est;
+                        p.dump_bnd[(size_t)row * p.dump_ld + q0 + qi] = b;
+                    }
+                }
+                if (flood && it < 2 && cb < nq) {
                     // Flood tiles: until the first prune every threshold is -inf and EVERY (row, query) pair is buffered:
                     // place them directly (slot = tile-local row), no atomics, no register select.
                     const uint32_t slot = it * ROWS + rt;
@@ -321,7 +345,7 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
                             float sc = fmaf(__uint_as_float(c < 32 ? v0[c & 31] : v1[c & 31]), mul, fmaf(ra, sh.qa[qi], rb * sh.qb[qi]));
                             if (euclid) { const float qn = sh.qn[qi]; sc -= EUC_KEEP * fmaf(qn, qn, x2); }
                             if (sc != sc) sc = INFINITY;
-                            my_cand[(size_t)qi * P + slot] = alive ? make_key(sc, grow) : 0ull;  // 0 = empty slot
+                            my_cand[(size_t)qi * P + slot] = (alive && sc >= p.min_score) ? make_key(sc, grow) : 0ull;  // 0 = empty slot
                         }
                     }
                     if (rt == 0 && chunk == 0)
@@ -375,12 +399,13 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
                 if (sh.cnt[qi] > prune_at) {
                     const float margin2 = bf16_margin2(p.metric, __uint_as_float(sh.max_ra), cosine ? 1.0f : __uint_as_float(sh.max_rb),
                                                        __uint_as_float(sh.maxxx), sh.qa[qi], sh.qb[qi], sh.qn[qi]);
-                    float floor_tau = -INFINITY;
+                    float floor_tau = p.min_score;
                     const uint32_t gt = __ldcg(p.gtau + q0 + qi);
-                    if (gt) floor_tau = ord_to_float(gt);
-                    warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, true, margin2, prune_at, floor_tau);
+                    if (gt) floor_tau = fmaxf(floor_tau, ord_to_float(gt));
+                    warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, true, margin2, prune_at, floor_tau,
+                                   nullptr, p.flags + FLAG_OVERFLOW);
                     // everything inside the margin must fit below prune_at, or the next tile could overflow the buffer
-                    if (lane == 0 && sh.cnt[qi] >= prune_at) atomicOr(p.flags + 1, 1);
+                    if (lane == 0 && sh.cnt[qi] >= prune_at) atomicOr(p.flags + FLAG_OVERFLOW, 1);
                     if (lane == 0 && sh.tau[qi] > -INFINITY) atomicMax(p.gtau + q0 + qi, ord_bits(sh.tau[qi]));
                 }
             group_sync(EPI_BAR, EPI_NT);
@@ -399,13 +424,23 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
         for (uint32_t qi = warp; qi < nq; qi += NTHREADS / 32) {
             const float margin2 = bf16_margin2(p.metric, __uint_as_float(sh.max_ra), cosine ? 1.0f : __uint_as_float(sh.max_rb),
                                                __uint_as_float(sh.maxxx), sh.qa[qi], sh.qb[qi], sh.qn[qi]);
-            float floor_tau = -INFINITY;
+            float floor_tau = p.min_score;
             const uint32_t gt = __ldcg(p.gtau + q0 + qi);
-            if (gt) floor_tau = ord_to_float(gt);
+            if (gt) floor_tau = fmaxf(floor_tau, ord_to_float(gt));
+            if (sh.cnt[qi] <= (int)p.k_emit) {
+                // few entries: no local selection (the finish kernel selects globally) — append what still reaches the
+                // current threshold
+                const float t = fmaxf(sh.tau[qi], floor_tau);
+                uint64_t thr = t > -INFINITY ? (uint64_t)ord_bits(t) << 32 : 1ull;
+                if (thr == 0ull) thr = 1ull;
+                warp_emit_above(my_cand + (size_t)qi * P, sh.cnt[qi], thr, lane, p.partial + (size_t)(q0 + qi) * p.list_cap,
+                                (int)p.list_cap, p.gcount + q0 + qi);
+                continue;
+            }
             warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane,
                            p.partial + (size_t)(q0 + qi) * p.list_cap, (int)p.list_cap, true, margin2,
-                           (int)p.k_emit, floor_tau, p.gcount + q0 + qi);
-            if (lane == 0 && sh.cnt[qi] >= (int)p.k_emit && (int)p.k_emit > (int)p.k) atomicOr(p.flags + 1, 2);
+                           (int)p.k_emit, floor_tau, p.gcount + q0 + qi, p.flags + FLAG_OVERFLOW);
+            if (lane == 0 && sh.cnt[qi] >= (int)p.k_emit && (int)p.k_emit > (int)p.k) atomicOr(p.flags + FLAG_OVERFLOW, 2);
             if (lane == 0 && sh.tau[qi] > -INFINITY) atomicMax(p.gtau + q0 + qi, ord_bits(sh.tau[qi]));
         }
         if (tid == 0) {
@@ -419,12 +454,16 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
     if (warp == 2) ptx::tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// The 16-bit pass needs a 16-bit image of the rows: the BF16 shadow of an fp32 shard, or — fp16 / bf16 corpora — the rows
+// themselves (a.shadow == a.rows, shadow_native: no rounding residue on the row side, only the per-row |x|^2 array).
 bool shadow_pass_supported(const DeviceInfo &di, const ScanArgs &a) {
-    return di.cc >= 100 && a.dtype == NK_DTYPE_F32 && a.shadow != nullptr && a.dim % 4 == 0 && a.dim >= 32 && a.k <= 192 &&
-           a.dim <= 32768 && (reinterpret_cast<uintptr_t>(a.rows) & 15) == 0 && a.n > 0;
+    if (di.cc < 100 || a.shadow == nullptr || a.xnorm2 == nullptr || a.k > 192 || a.dim > 32768 || a.dim < 32 || a.n == 0) return false;
+    if ((reinterpret_cast<uintptr_t>(a.rows) & 15) != 0 || (reinterpret_cast<uintptr_t>(a.shadow) & 15) != 0) return false;
+    if (a.dtype == NK_DTYPE_F32) return a.dim % 4 == 0;
+    return a.dim % 8 == 0;  // 16-bit rows: 16-byte TMA row stride and 128-bit exact re-scoring loads
 }
 
-// Host: convert the queries of this search once (all passes share the array).
+// Host: stand-alone bf16 conversion of a query block (assign_tensor.cu: the centroids).
 int bf16_prep_queries(const ScanArgs &a, uint32_t Qpad, uint32_t dimpad, float acc_c, void *qbf16, float *qnorm, float *qa,
                       float *qb, uint64_t *launches) {
     bf16_prep_queries_kernel<<<Qpad, 256, 0, a.stream>>>(a.queries, a.Q, a.dim, dimpad, a.metric == NK_METRIC_COSINE, acc_c,
@@ -434,39 +473,40 @@ int bf16_prep_queries(const ScanArgs &a, uint32_t Qpad, uint32_t dimpad, float a
     return 0;
 }
 
-template <int QT>
-static int launch_shadow_pass_t(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint32_t grid, uint32_t k_emit,
-                                const void *qbf16, uint32_t dimpad, const float *qnorm, const float *qa, const float *qb,
-                                uint32_t Qpad, uint32_t q0, uint32_t nq, uint32_t qgroups, uint64_t *launches) {
+template <int QT, bool DUMP>
+static int launch_shadow_pass_t(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, const ShadowPassArgs &sp, uint64_t *launches) {
     using namespace sb;
-    CUtensorMap map_rows, map_q;
-    if (tc_make_map(&map_rows, a.shadow, a.n, dimpad, 2, BKB, ROWS, (uint64_t)dimpad * 2)) return -1;
-    if (tc_make_map(&map_q, qbf16, Qpad, dimpad, 2, BKB, QT, (uint64_t)dimpad * 2)) return -1;  // rows past Qpad: zero
+    const bool native = a.shadow_native;  // 16-bit corpus scanned in place: row stride dim * 2, columns past dim read as zero (TMA OOB fill)
+    const CUtensorMap *map_rows = tc_cached_map(ws, 4, a.shadow, a.n, native ? a.dim : sp.dimpad, 2, BKB, ROWS,
+                                                (uint64_t)(native ? a.dim : sp.dimpad) * 2, a.dtype);
+    const CUtensorMap *map_q = tc_cached_map(ws, QT == 64 ? 5 : 6, sp.qbf16, sp.Qpad, sp.dimpad, 2, BKB, QT, (uint64_t)sp.dimpad * 2,
+                                             a.dtype);  // rows past Qpad: zero
+    if (!map_rows || !map_q) return -1;
     const size_t smem = (size_t)Cfg<QT>::RING_BYTES + sizeof(Shared) + 1024;
     if (smem > di.max_smem_optin) {
         set_error("shadow tensor path needs %zu B shared memory (> %zu)", smem, di.max_smem_optin);
         return -1;
     }
-    NK_CUDA_OK(cudaFuncSetAttribute(knn_scan_shadow_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    tc::Params p;
-    p.n = a.n; p.dim = a.dim; p.nslab = dimpad / BKB; p.row_base = a.row_base;
-    p.q0 = q0; p.nq = nq; p.k = a.k; p.qpad_off = q0; p.qgroups = qgroups; p.list_cap = grid * k_emit;
-    p.metric = a.metric; p.k_emit = k_emit; p.margin_c = 0.0f; p.qnorm = qnorm; p.qa = qa; p.qb = qb;
+    if (tc_ensure_smem(reinterpret_cast<const void *>(knn_scan_shadow_kernel<QT, DUMP>), di.device_id, smem)) return -1;
+    tc::Params p{};
+    p.n = a.n; p.dim = a.dim; p.nslab = sp.dimpad / BKB; p.row_base = a.row_base;
+    p.q0 = sp.q0; p.nq = sp.nq; p.k = a.k; p.qpad_off = sp.q0; p.qgroups = sp.qgroups; p.list_cap = sp.grid * sp.k_emit;
+    p.metric = a.metric; p.k_emit = sp.k_emit; p.margin_c = 0.0f; p.qnorm = sp.qnorm; p.qa = sp.qa; p.qb = sp.qb;
     p.xnorm2 = a.xnorm2; p.dnorm2 = a.dnorm2;
     p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = nullptr; p.debug = tc_debug_flags(); p.mask = a.row_mask;
-    p.gtau = reinterpret_cast<uint32_t *>(ws.keys2); p.gcount = reinterpret_cast<int *>(ws.keys2) + (Qpad + QT_BIG);
-    knn_scan_shadow_kernel<QT><<<grid, NTHREADS, smem, a.stream>>>(map_rows, map_q, p);
+    p.gtau = reinterpret_cast<uint32_t *>(ws.keys2); p.gcount = reinterpret_cast<int *>(ws.keys2) + (sp.Qpad + QT_BIG);
+    p.presampled = sp.presampled; p.min_score = a.min_score; p.op_f16 = a.dtype == NK_DTYPE_F16;
+    p.dump_est = sp.dump_est; p.dump_bnd = sp.dump_bnd; p.dump_ld = sp.dump_ld;
+    knn_scan_shadow_kernel<QT, DUMP><<<sp.grid, NTHREADS, smem, a.stream>>>(*map_rows, *map_q, p);
     NK_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
     if (a.main_launches) ++*a.main_launches;
     return 0;
 }
 
-int launch_shadow_pass(int qt, const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint32_t grid, uint32_t k_emit,
-                       const void *qbf16, uint32_t dimpad, const float *qnorm, const float *qa, const float *qb, uint32_t Qpad,
-                       uint32_t q0, uint32_t nq, uint32_t qgroups, uint64_t *launches) {
-    return qt == 128 ? launch_shadow_pass_t<128>(di, a, ws, grid, k_emit, qbf16, dimpad, qnorm, qa, qb, Qpad, q0, nq, qgroups, launches)
-                     : launch_shadow_pass_t<64>(di, a, ws, grid, k_emit, qbf16, dimpad, qnorm, qa, qb, Qpad, q0, nq, qgroups, launches);
+int launch_shadow_pass(int qt, const DeviceInfo &di, const ScanArgs &a, Workspace &ws, const ShadowPassArgs &sp, uint64_t *launches) {
+    if (sp.dump_est) return launch_shadow_pass_t<64, true>(di, a, ws, sp, launches);
+    return qt == 128 ? launch_shadow_pass_t<128, false>(di, a, ws, sp, launches) : launch_shadow_pass_t<64, false>(di, a, ws, sp, launches);
 }
 
 }  // namespace nk

@@ -7,6 +7,21 @@
 
 namespace nk {
 
+// Device status words of one shard (Workspace::flags, NK_FLAG_WORDS ints).  filter_prep_kernel clears [1..7] at the start of
+// every filter search; [0] is sticky until the host reads it; [8..] are cumulative diagnostics.
+enum {
+    FLAG_FATAL = 0,       // candidate-buffer overflow (must stay 0)
+    FLAG_OVERFLOW = 1,    // a filter stage overflowed its margin buffers / met non-finite bounds -> next stage
+    FLAG_MAXXX = 2,       // float bits: max |x|^2 seen
+    FLAG_FINISH_CTAS = 3, // filter_finish_kernel: CTAs done (the last one does the stage bookkeeping)
+    FLAG_MAX_RA = 4,      // float bits: BF16 max ra
+    FLAG_RETRY = 5,       // retry-stage marker (stage 2 runs only if set)
+    FLAG_MAX_RB = 6,      // float bits: BF16 max rb
+    FLAG_LONGEST = 7,     // longest shared list of this search (diagnostics)
+    FLAG_N_RETRY = 8,     // cumulative: searches whose first (BF16) stage overflowed
+    FLAG_N_EXACT = 9,     // cumulative: searches that fell through to the exact kernels
+    NK_FLAG_WORDS = 16
+};
 namespace tc {
 constexpr int THREADS = 512;
 constexpr int BK = 32;           // floats per corpus K-slab = one 128-byte swizzle row
@@ -35,12 +50,20 @@ struct Params {
     uint64_t *partial;        // exact: [Q][grid][k_emit] fixed slots; filter: [Q][grid*k_emit] shared append lists
     uint32_t *gtau;           // filter: [Q] cross-CTA shared threshold (order-preserving bits, atomicMax; 0 = none yet)
     int *gcount;              // filter: [Q] fill of the shared append lists
-    int *flags;               // [0] fatal buffer overflow, [1] filter-margin overflow (-> next stage), [2] max |x|^2 bits,
-                              // [4] / [6] BF16 max ra / rb bits, [5] retry-stage marker, [7] longest list (diagnostics)
+    int *flags;               // status words, layout in FLAG_* below
     const int *only_if;       // exact fallback: run only if *only_if != 0
     const uint32_t *mask;     // row bitmask (bit set = row takes part) or nullptr
     int debug;                // NK_TC_DEBUG bit 64: clock64 wait-time instrumentation of CTA 0
+    int presampled;           // filter: gtau[] already holds a sampled lower bound of every query's k-th best score
+                              // (filter_prep_kernel): no flood tiles, thresholds are adopted at kernel start
+    float min_score;          // filter: caller's score floor (VectorIndex minSimilarity, vector_index.go:339-352): rows
+                              // whose upper bound is below it are never buffered (-inf = none)
+    float *dump_est, *dump_bnd;  // DUMP kernels only (tests): per (row, query) score estimate and error bound, [n][dump_ld]
+    uint32_t dump_ld;
+    int op_f16;               // 16-bit kernel: operands are fp16 (an fp16 corpus scanned in place) instead of bf16
 };
+
+
 }  // namespace tc
 
 #ifdef __CUDACC__
@@ -63,15 +86,29 @@ __device__ __forceinline__ float bf16_margin2(int metric, float max_ra, float ma
 
 // 2-D row-major [rows x cols] tensor of 4-byte (fp32) or 2-byte (bf16) elements, box = [box_rows x box_cols] with
 // box_cols * elem_bytes == 128 (one swizzle row), 128-byte swizzle, OOB -> 0.
+// map_dtype (2-byte elements only): NK_DTYPE_F16 -> fp16 tensor, anything else -> bf16.
 int tc_make_map(CUtensorMap *m, const void *base, uint64_t rows, uint32_t cols, uint32_t elem_bytes, uint32_t box_cols,
-                uint32_t box_rows, uint64_t row_stride_bytes);
+                uint32_t box_rows, uint64_t row_stride_bytes, int map_dtype = 0);
+int tc_ensure_smem(const void *func, int device, size_t smem);
 int tc_debug_flags();
 
+// Cached tensor map: cuTensorMapEncodeTiled runs only when (base, shape, box) changed since the last search.
+const CUtensorMap *tc_cached_map(Workspace &ws, int slot, const void *base, uint64_t rows, uint32_t cols, uint32_t elem_bytes,
+                                 uint32_t box_cols, uint32_t box_rows, uint64_t row_stride_bytes, int map_dtype = 0);
+int tc_env_int(const char *name, int dflt);  // getenv once per name (read at first use)
+
 // BF16 shadow filter pass (scan_tensor_shadow.cu): queries [q0, q0+nq), nq <= qgroups * qt, qt = 64 or 128.
-int launch_shadow_pass(int qt, const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint32_t grid, uint32_t k_emit,
-                       const void *qbf16, uint32_t dimpad, const float *qnorm, const float *qa, const float *qb, uint32_t Qpad,
-                       uint32_t q0, uint32_t nq, uint32_t qgroups, uint64_t *launches);
+struct ShadowPassArgs {
+    uint32_t grid, k_emit, dimpad, Qpad, q0, nq, qgroups;
+    const void *qbf16;
+    const float *qnorm, *qa, *qb;
+    int presampled;
+    float *dump_est = nullptr, *dump_bnd = nullptr;  // test-only DUMP instantiation
+    uint32_t dump_ld = 0;
+};
+int launch_shadow_pass(int qt, const DeviceInfo &di, const ScanArgs &a, Workspace &ws, const ShadowPassArgs &sp, uint64_t *launches);
 bool shadow_pass_supported(const DeviceInfo &di, const ScanArgs &a);
+// stand-alone bf16 conversion of a query block (k-means assignment: centroids as "queries")
 int bf16_prep_queries(const ScanArgs &a, uint32_t Qpad, uint32_t dimpad, float acc_c, void *qbf16, float *qnorm, float *qa,
                       float *qb, uint64_t *launches);
 // fp32 rows [first, first+count) -> bf16 shadow rows (stride dimpad) + |x|^2, |x - bf16(x)|^2

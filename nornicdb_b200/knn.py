@@ -13,7 +13,7 @@ import numpy as np
 from . import _lib
 
 METRICS = {"cosine": 0, "dot": 1, "euclidean": 2}
-DTYPES = {"f32": 0, "fp32": 0, "float32": 0, "f16": 1, "fp16": 1, "float16": 1}
+DTYPES = {"f32": 0, "fp32": 0, "float32": 0, "f16": 1, "fp16": 1, "float16": 1, "bf16": 2, "bfloat16": 2}
 PATHS = {"auto": 0, "simt": 1, "tensor": 2, "filter": 3, "shadow": 4}
 NK_MAX_K = 1024
 
@@ -34,7 +34,8 @@ class KnnIndex:
         self.dim = int(dim)
         self.metric = metric
         self.dtype = DTYPES[dtype]
-        self.np_dtype = np.float16 if self.dtype == 1 else np.float32
+        # bf16 rows travel as raw uint16 bit patterns (numpy has no bfloat16): see to_bf16_bits / from_bf16_bits
+        self.np_dtype = np.float16 if self.dtype == 1 else np.uint16 if self.dtype == 2 else np.float32
         self.devices = list(devices)
         ids = (C.c_int * len(self.devices))(*self.devices)
         self.ptr = self.lib.nk_index_create(ids, len(self.devices), self.dim, self.dtype, METRICS[metric])
@@ -60,6 +61,8 @@ class KnnIndex:
 
     # -- corpus ------------------------------------------------------------------------------------
     def _rows(self, rows) -> np.ndarray:
+        if self.dtype == 2 and np.asarray(rows).dtype.kind == "f":
+            rows = to_bf16_bits(rows)  # float input to a bf16 index: round to nearest even, like the device does
         a = np.ascontiguousarray(np.asarray(rows, dtype=self.np_dtype))
         if a.size % self.dim:
             raise KnnError("rows are not a multiple of dim")
@@ -102,6 +105,68 @@ class KnnIndex:
 
     def fill_uniform(self, n_rows: int, seed: int) -> None:
         _check(self.lib.nk_index_fill_uniform(self.ptr, int(n_rows), int(seed)), "nk_index_fill_uniform")
+
+    def fill_clustered(self, n_rows: int, seed: int, n_centres: int = 1000, sigma: float = 0.1, unit_norm: bool = False) -> None:
+        """SURVEY.md 8(d)'s Gaussian-mixture corpus, generated on the device (near-tie stress case)."""
+        _check(self.lib.nk_index_fill_clustered(self.ptr, int(n_rows), int(seed), int(n_centres), float(sigma), 1 if unit_norm else 0),
+               "nk_index_fill_clustered")
+
+    def refresh_shadow(self) -> None:
+        _check(self.lib.nk_index_refresh_shadow(self.ptr), "nk_index_refresh_shadow")
+
+    def set_metric(self, metric: str) -> None:
+        _check(self.lib.nk_index_set_metric(self.ptr, METRICS[metric]), "nk_index_set_metric")
+        self.metric = metric
+
+    def set_min_score(self, min_score: Optional[float]) -> None:
+        """Score floor evaluated inside the kernels (cosine / dot: minimum similarity; euclidean: maximum distance).
+        None clears it."""
+        if min_score is None:
+            min_score = float("inf") if self.metric == "euclidean" else float("-inf")
+        _check(self.lib.nk_index_set_min_score(self.ptr, float(min_score)), "nk_index_set_min_score")
+
+    def set_row_groups(self, group_of_row, n_groups: Optional[int] = None) -> None:
+        if group_of_row is None:
+            _check(self.lib.nk_index_set_row_groups(self.ptr, None, 0, 0), "nk_index_set_row_groups")
+            return
+        g = np.ascontiguousarray(np.asarray(group_of_row, dtype=np.uint32).reshape(-1))
+        ng = int(g.max()) + 1 if n_groups is None and g.size else int(n_groups or 1)
+        _check(self.lib.nk_index_set_row_groups(self.ptr, g.ctypes.data_as(C.c_void_p), int(g.size), ng), "nk_index_set_row_groups")
+
+    def search_groups(self, query, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """Best-of-chunks per node: (node ids, rows of their best chunks, scores), best first."""
+        q = np.ascontiguousarray(np.asarray(query, dtype=np.float32).reshape(-1))
+        if q.size != self.dim:
+            raise KnnError(f"invalid dimensions: query has {q.size}, index has {self.dim}")
+        k = int(k)
+        if k <= 0:
+            return np.empty(0, np.uint32), np.empty(0, np.uint32), np.empty(0, np.float32)
+        grp = np.empty(k, dtype=np.uint32); row = np.empty(k, dtype=np.uint32); sc = np.empty(k, dtype=np.float32)
+        n = _check(self.lib.nk_search_groups(self.ptr, q.ctypes.data_as(C.c_void_p), k, grp.ctypes.data_as(C.c_void_p),
+                                             row.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p)), "nk_search_groups")
+        return grp[:n], row[:n], sc[:n]
+
+    def debug_counters(self) -> dict:
+        out = (C.c_uint64 * 4)()
+        _check(self.lib.nk_index_debug_counters(self.ptr, out), "nk_index_debug_counters")
+        return {"bf16_stage_retries": int(out[0]), "exact_stage_runs": int(out[1]), "longest_list": int(out[2])}
+
+    def filter_dump(self, queries, which: str = "shadow") -> Tuple[np.ndarray, np.ndarray]:
+        """Tests only: (estimate, bound) arrays [rows x Q] of the filter kernel `which` ("shadow" | "filter")."""
+        q = np.ascontiguousarray(np.asarray(queries, dtype=np.float32)).reshape(-1, self.dim)
+        n = len(self)
+        est = np.empty((n, q.shape[0]), dtype=np.float32)
+        bnd = np.empty((n, q.shape[0]), dtype=np.float32)
+        _check(self.lib.nk_debug_filter_dump(self.ptr, q.ctypes.data_as(C.c_void_p), q.shape[0], PATHS[which],
+                                             est.ctypes.data_as(C.c_void_p), bnd.ctypes.data_as(C.c_void_p)), "nk_debug_filter_dump")
+        return est, bnd
+
+    def status(self, stream: int = 0) -> None:
+        _check(self.lib.nk_index_status(self.ptr, stream), "nk_index_status")
+
+    def search_sharded_device(self, comm: "Comm", q_ptr: int, Q: int, k: int, out_idx_ptr: int, out_score_ptr: int, stream: int = 0) -> int:
+        return _check(self.lib.nk_search_sharded_device(self.ptr, comm.ptr, q_ptr, Q, k, out_idx_ptr, out_score_ptr, stream),
+                      "nk_search_sharded_device")
 
     def set_row_base(self, row_base: int) -> None:
         _check(self.lib.nk_index_set_row_base(self.ptr, int(row_base)), "nk_index_set_row_base")
@@ -205,6 +270,51 @@ class KnnIndex:
         _check(self.lib.nk_index_cluster_means(self.ptr, a.ctypes.data_as(C.c_void_p), c.shape[0], c.ctypes.data_as(C.c_void_p),
                                                counts.ctypes.data_as(C.c_void_p)), "nk_index_cluster_means")
         return c, counts
+
+
+def to_bf16_bits(a) -> np.ndarray:
+    """fp32 array -> bf16 bit patterns (uint16), round to nearest even (what the device conversion does)."""
+    u = np.ascontiguousarray(np.asarray(a, dtype=np.float32)).view(np.uint32)
+    r = ((u >> 16) & 1) + np.uint32(0x7FFF)
+    return ((u + r) >> 16).astype(np.uint16)
+
+
+def from_bf16_bits(b) -> np.ndarray:
+    return (np.asarray(b, dtype=np.uint16).astype(np.uint32) << 16).view(np.float32)
+
+
+class Comm:
+    """One rank's exchange context of a row-sharded search (nk_comm_*): candidate lists cross GPUs by peer stores."""
+
+    def __init__(self, device: int, rank: int, world: int, slot_bytes: int):
+        self.lib = _lib.load()
+        self.rank, self.world = rank, world
+        self.ptr = self.lib.nk_comm_create(int(device), int(rank), int(world), int(slot_bytes))
+        if not self.ptr:
+            raise KnnError(f"nk_comm_create: {_lib.last_error()}")
+
+    def export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(self.lib.nk_comm_export(self.ptr, buf), "nk_comm_export")
+        return bytes(buf.raw)
+
+    def connect(self, handles: Sequence[bytes]) -> None:
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.world
+        _check(self.lib.nk_comm_connect(self.ptr, C.c_char_p(blob)), "nk_comm_connect")
+
+    @staticmethod
+    def connect_local(comms: Sequence["Comm"]) -> None:
+        arr = (C.c_void_p * len(comms))(*[c.ptr for c in comms])
+        _check(_lib.load().nk_comm_connect_local(arr, len(comms)), "nk_comm_connect_local")
+
+    def status(self, stream: int = 0) -> None:
+        _check(self.lib.nk_comm_status(self.ptr, stream), "nk_comm_status")
+
+    def release(self) -> None:
+        if self.ptr:
+            self.lib.nk_comm_release(self.ptr)
+            self.ptr = None
 
 
 def blob_vectors(data: bytes) -> Tuple[int, int, int]:
