@@ -190,7 +190,9 @@ int nk_index_stats(const NkIndex *ix, NkStats *out);
 int nk_index_debug_flags(NkIndex *ix, int out[4]);
 /* Cumulative diagnostics of shard 0: out[0] = filter searches whose first (16-bit) stage overflowed its margin buffers and
  * re-ran through the TF32 filter, out[1] = filter searches that fell through to the exact kernels, out[2] = longest
- * per-query survivor list of the last filter search.  (Retry rate of a corpus = out[0..1] / searches.) */
+ * per-query survivor list of the last filter search, out[3] = OR of the overflow reasons seen so far (1 = a margin buffer
+ * could not be pruned below its refill mark, 2 = a CTA's emission was cut at its slot count, 8 = non-finite bound).
+ * (Retry rate of a corpus = out[0..1] / searches.) */
 int nk_index_debug_counters(NkIndex *ix, uint64_t out[4]);
 /* Tests only: the raw score estimate and the error bound the filter kernels compare with, for EVERY (row, query) pair of
  * a single-device index: est_host / bnd_host are [rows x Q] floats (row-major, Q <= 64).  which = NK_PATH_TENSOR_FILTER

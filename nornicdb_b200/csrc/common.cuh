@@ -33,6 +33,21 @@ void clear_error();
         }                                                                                     \
     } while (0)
 
+// Every entry point binds the device it needs (cudaSetDevice per call, so callers may hop OS threads) and puts the caller's
+// current device back on return: hosts that track the current device themselves (PyTorch, CuPy) never see it move.
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            prev = -1;
+            cudaGetLastError();
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 #define NK_CUDA_OK_PTR(call)                                                                  \
     do {                                                                                      \
         cudaError_t _e = (call);                                                              \
@@ -214,7 +229,16 @@ __device__ __forceinline__ void warp_prune(uint64_t *cand, int *cnt, float *tau,
     __syncwarp();
     uint64_t thr_key = 1ull;  // keep every live key
     float new_tau = -INFINITY;
-    if (n >= (int)k) {
+    // margin mode: keys with bound +inf are rows whose score is undecidable (NaN); they are kept but say nothing about the
+    // k-th best score, so the threshold comes from the k-th largest FINITE bound = the (k + n_inf)-th largest key
+    int k_eff = (int)k;
+    if (margin_mode) {
+        int inf_mine = 0;
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) inf_mine += v[i] >= (0xFF800000ull << 32) ? 1 : 0;
+        k_eff += __reduce_add_sync(0xffffffffu, inf_mine);
+    }
+    if (n >= k_eff) {
         uint64_t prefix = 0ull;
         const int low = margin_mode ? 32 : 0;
 #pragma unroll 1
@@ -223,7 +247,7 @@ __device__ __forceinline__ void warp_prune(uint64_t *cand, int *cnt, float *tau,
             int mine = 0;
 #pragma unroll
             for (int i = 0; i < PER_LANE; ++i) mine += v[i] >= c ? 1 : 0;
-            if (__reduce_add_sync(0xffffffffu, mine) >= (int)k) prefix = c;
+            if (__reduce_add_sync(0xffffffffu, mine) >= k_eff) prefix = c;
         }
         if (prefix == 0ull) {
             // fewer than k LIVE keys (empty slots are key 0): keep them all, no threshold yet

@@ -58,6 +58,7 @@ __global__ void exchange_push_kernel(PushParams p) {
 extern "C" {
 
 NkComm *nk_comm_create(int device_id, int rank, int world, size_t slot_bytes) {
+    nk::DeviceGuard _restore_device;
     if (world < 1 || world > 64 || rank < 0 || rank >= world || slot_bytes == 0) {
         nk::set_error("nk_comm_create: bad arguments (1 <= world <= 64, 0 <= rank < world, slot_bytes > 0)");
         return nullptr;
@@ -86,6 +87,7 @@ NkComm *nk_comm_create(int device_id, int rank, int world, size_t slot_bytes) {
 }
 
 int nk_comm_export(NkComm *c, void *handle_out) {
+    nk::DeviceGuard _restore_device;
     if (!c || !handle_out) { nk::set_error("null argument"); return -1; }
     static_assert(sizeof(cudaIpcMemHandle_t) == NK_COMM_HANDLE_BYTES, "IPC handle size");
     NK_CUDA_OK(cudaSetDevice(c->device));
@@ -96,6 +98,7 @@ int nk_comm_export(NkComm *c, void *handle_out) {
 }
 
 int nk_comm_connect(NkComm *c, const void *handles) {
+    nk::DeviceGuard _restore_device;
     if (!c || !handles) { nk::set_error("null argument"); return -1; }
     NK_CUDA_OK(cudaSetDevice(c->device));
     for (int r = 0; r < c->world; ++r) {
@@ -112,6 +115,7 @@ int nk_comm_connect(NkComm *c, const void *handles) {
 }
 
 int nk_comm_connect_local(NkComm **comms, int world) {
+    nk::DeviceGuard _restore_device;
     if (!comms || world < 1) { nk::set_error("null argument"); return -1; }
     for (int a = 0; a < world; ++a) {
         if (!comms[a] || comms[a]->world != world || comms[a]->rank != a) { nk::set_error("nk_comm_connect_local: comms must be in rank order"); return -1; }
@@ -134,6 +138,7 @@ int nk_comm_connect_local(NkComm **comms, int world) {
 }
 
 void nk_comm_release(NkComm *c) {
+    nk::DeviceGuard _restore_device;
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
@@ -146,6 +151,7 @@ void nk_comm_release(NkComm *c) {
 
 // Device-side state of the last exchange: 0 ok, 2 = a peer did not arrive within the timeout.  Synchronises `stream`.
 int nk_comm_status(NkComm *c, void *stream) {
+    nk::DeviceGuard _restore_device;
     if (!c) { nk::set_error("null argument"); return -1; }
     NK_CUDA_OK(cudaSetDevice(c->device));
     NK_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
@@ -162,6 +168,7 @@ int nk_comm_status(NkComm *c, void *stream) {
 // keys_dev: this rank's [Q x k] keys (device, produced earlier on `stream`); writes the merged, decoded result.
 int nk_comm_exchange_merge(NkComm *c, const uint64_t *keys_dev, uint32_t Q, uint32_t k, int metric, uint32_t *out_idx_dev,
                            float *out_score_dev, void *stream) {
+    nk::DeviceGuard _restore_device;
     if (!c || !keys_dev || !out_idx_dev || !out_score_dev) { nk::set_error("null argument"); return -1; }
     if (!c->connected) { nk::set_error("exchange: communicator is not connected"); return -1; }
     if (Q == 0 || k == 0) return 0;

@@ -56,6 +56,8 @@ struct NkShard {
     nk::Workspace ws;
     uint64_t *h_keys = nullptr;  // pinned staging for multi-shard host merge
     size_t h_keys_bytes = 0;
+    unsigned char *h_res = nullptr;  // pinned staging of a single-shard result: [idx][score][status words] in ONE sync
+    size_t h_res_bytes = 0;
     // cold-start feed: two pinned staging buffers + their "copy drained" events (stream_h2d)
     void *stage[2] = {nullptr, nullptr};
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
@@ -401,6 +403,7 @@ const char *nk_last_error(void) { return nk::get_error(); }
 const char *nk_version(void) { return "nornic-knn-b200 0.1 (sm_100a)"; }
 
 NkIndex *nk_index_create(const int *device_ids, int n_devices, uint32_t dim, int dtype, int metric) {
+    nk::DeviceGuard _restore_device;
     if (n_devices <= 0 || !device_ids || dim == 0) {
         nk::set_error("nk_index_create: need >= 1 device and dim > 0");
         return nullptr;
@@ -437,6 +440,7 @@ NkIndex *nk_index_create(const int *device_ids, int n_devices, uint32_t dim, int
 }
 
 void nk_index_release(NkIndex *ix) {
+    nk::DeviceGuard _restore_device;
     if (!ix) return;
     for (auto &s : ix->shards) {
         cudaSetDevice(s.device);
@@ -447,6 +451,7 @@ void nk_index_release(NkIndex *ix) {
         if (s.rows && s.owns) cudaFree(s.rows);
         shard_drop_shadow(s);
         if (s.h_keys) cudaFreeHost(s.h_keys);
+        if (s.h_res) cudaFreeHost(s.h_res);
         for (int i = 0; i < 2; ++i) {
             if (s.stage[i]) cudaFreeHost(s.stage[i]);
             if (s.stage_ev[i]) cudaEventDestroy(s.stage_ev[i]);
@@ -460,6 +465,7 @@ void nk_index_release(NkIndex *ix) {
 }
 
 static int upload_impl(NkIndex *ix, const void *rows_host, uint64_t n_rows, bool src_is_f32) {
+    nk::DeviceGuard _restore_device;
     if (!ix) { nk::set_error("null index"); return -1; }
     if (n_rows && !rows_host) { nk::set_error("null rows"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
@@ -519,6 +525,7 @@ int nk_blob_vectors(const void *blob, size_t blob_bytes, uint32_t *dims, uint32_
 }
 
 int nk_index_append(NkIndex *ix, const void *rows_host, uint64_t n_rows) {
+    nk::DeviceGuard _restore_device;
     if (!ix) { nk::set_error("null index"); return -1; }
     if (n_rows == 0) return 0;
     if (!rows_host) { nk::set_error("null rows"); return -1; }
@@ -539,6 +546,7 @@ int nk_index_append(NkIndex *ix, const void *rows_host, uint64_t n_rows) {
 }
 
 int nk_index_update_row(NkIndex *ix, uint64_t row, const void *row_host) {
+    nk::DeviceGuard _restore_device;
     if (!ix || !row_host) { nk::set_error("null argument"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
     uint64_t local;
@@ -554,6 +562,7 @@ int nk_index_update_row(NkIndex *ix, uint64_t row, const void *row_host) {
 }
 
 int nk_index_remove_swap(NkIndex *ix, uint64_t row) {
+    nk::DeviceGuard _restore_device;
     if (!ix) { nk::set_error("null index"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
     uint64_t total = ix->rows();
@@ -589,6 +598,7 @@ int nk_index_remove_swap(NkIndex *ix, uint64_t row) {
 }
 
 static int fill_impl(NkIndex *ix, uint64_t n_rows, uint64_t seed, uint32_t centres, float sigma, int unit) {
+    nk::DeviceGuard _restore_device;
     if (!ix) { nk::set_error("null index"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
     drop_row_mask(ix);
@@ -626,6 +636,7 @@ int nk_index_fill_clustered(NkIndex *ix, uint64_t n_rows, uint64_t seed, uint32_
 }
 
 int nk_index_set_row_base(NkIndex *ix, uint64_t row_base) {
+    nk::DeviceGuard _restore_device;
     if (!ix) { nk::set_error("null index"); return -1; }
     if (ix->shards.size() != 1) { nk::set_error("row_base applies to single-device indexes"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
@@ -635,6 +646,7 @@ int nk_index_set_row_base(NkIndex *ix, uint64_t row_base) {
 }
 
 int nk_index_attach_device_rows(NkIndex *ix, void *rows_dev, uint64_t n_rows) {
+    nk::DeviceGuard _restore_device;
     if (!ix) { nk::set_error("null index"); return -1; }
     if (ix->shards.size() != 1) { nk::set_error("attach applies to single-device indexes"); return -1; }
     if (ix->row_base + n_rows > 0xfffffff0ull) { nk::set_error("index exceeds 2^32 rows (row ids are uint32)"); return -1; }
@@ -656,6 +668,7 @@ int nk_index_attach_device_rows(NkIndex *ix, void *rows_dev, uint64_t n_rows) {
 // explicit "rows are final" signal that gives the documented drop-in route the fast filter path; for library-owned shards
 // it is a no-op unless rows were changed behind the library's back.
 int nk_index_refresh_shadow(NkIndex *ix) {
+    nk::DeviceGuard _restore_device;
     if (!ix) { nk::set_error("null index"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
     for (auto &s : ix->shards) {
@@ -688,10 +701,12 @@ int nk_index_set_min_score(NkIndex *ix, float min_score) {
 // tombstones): bit r of mask_words (LSB first in 32-bit words) set = row r (relative to the index's first row) may be
 // returned.  NULL clears the filter.  Row-count changing mutations (upload, append, remove_swap, fill, attach) clear it.
 int nk_index_set_row_mask(NkIndex *ix, const uint32_t *mask_words, uint64_t n_bits) {
+    nk::DeviceGuard _restore_device;
     if (!ix) { nk::set_error("null index"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
-    if (!mask_words) {
-        drop_row_mask(ix);
+    if (!mask_words) {  // clear the filter only (the row groups stay: the row count did not change)
+        ix->mask_on = false;
+        for (auto &s : ix->shards) s.mask_on = false;
         return 0;
     }
     if (n_bits != ix->rows()) { nk::set_error("row mask has %llu bits, index has %llu rows", (unsigned long long)n_bits, (unsigned long long)ix->rows()); return -1; }
@@ -735,6 +750,7 @@ int nk_index_stats(const NkIndex *ix, NkStats *out) {
 }
 
 int nk_index_debug_flags(NkIndex *ix, int out[4]) {
+    nk::DeviceGuard _restore_device;
     if (!ix || !out || ix->shards.empty()) { nk::set_error("null argument"); return -1; }
     NkShard &s = ix->shards[0];
     NK_CUDA_OK(cudaSetDevice(s.device));
@@ -749,13 +765,14 @@ int nk_index_debug_flags(NkIndex *ix, int out[4]) {
 // through the TF32 filter, out[1] = filter searches that fell through to the exact kernels, out[2] = longest per-query
 // survivor list of the last filter search.  bench.py reports out[0..1] / searches as the retry rate of a corpus.
 int nk_index_debug_counters(NkIndex *ix, uint64_t out[4]) {
+    nk::DeviceGuard _restore_device;
     if (!ix || !out || ix->shards.empty()) { nk::set_error("null argument"); return -1; }
     NkShard &s = ix->shards[0];
     NK_CUDA_OK(cudaSetDevice(s.device));
     NK_CUDA_OK(cudaDeviceSynchronize());
     int h[nk::NK_FLAG_WORDS];
     NK_CUDA_OK(cudaMemcpy(h, s.ws.flags, sizeof(h), cudaMemcpyDeviceToHost));
-    out[0] = (uint64_t)h[nk::FLAG_N_RETRY]; out[1] = (uint64_t)h[nk::FLAG_N_EXACT]; out[2] = (uint64_t)h[nk::FLAG_LONGEST]; out[3] = 0;
+    out[0] = (uint64_t)h[nk::FLAG_N_RETRY]; out[1] = (uint64_t)h[nk::FLAG_N_EXACT]; out[2] = (uint64_t)h[nk::FLAG_LONGEST]; out[3] = (uint64_t)h[nk::FLAG_OVF_BITS];
     return 0;
 }
 
@@ -763,6 +780,7 @@ int nk_index_debug_counters(NkIndex *ix, uint64_t out[4]) {
 // single-device index (rows x Q floats each, row-major [row][query], host buffers).  which = NK_PATH_TENSOR_FILTER (TF32
 // pass over fp32 rows) or NK_PATH_TENSOR_SHADOW (16-bit pass).  The filters are sound iff |est - exact score| <= bnd.
 int nk_debug_filter_dump(NkIndex *ix, const float *queries_host, uint32_t Q, int which, float *est_host, float *bnd_host) {
+    nk::DeviceGuard _restore_device;
     NkShard *s;
     if (!ix || ix->shards.size() != 1) { nk::set_error("single-device index required"); return -1; }
     s = &ix->shards[0];
@@ -809,6 +827,7 @@ int nk_index_enable_timing(NkIndex *ix, int enabled) {
 }
 
 int nk_index_scan_time_ms(NkIndex *ix, double *total_ms, uint64_t *scan_launches) {
+    nk::DeviceGuard _restore_device;
     if (!ix || !total_ms || !scan_launches) { nk::set_error("null argument"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
     double ms = 0.0;
@@ -833,6 +852,7 @@ int nk_index_scan_time_ms(NkIndex *ix, double *total_ms, uint64_t *scan_launches
 }
 
 int nk_index_read_rows(NkIndex *ix, uint64_t row, uint64_t n_rows, void *rows_host) {
+    nk::DeviceGuard _restore_device;
     if (!ix || (!rows_host && n_rows)) { nk::set_error("null argument"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
     const size_t rb = (size_t)ix->dim * ix->esz();
@@ -850,6 +870,7 @@ int nk_index_read_rows(NkIndex *ix, uint64_t row, uint64_t n_rows, void *rows_ho
 }
 
 int nk_search(NkIndex *ix, const float *queries_host, uint32_t Q, uint32_t k, uint32_t *out_idx, float *out_score) {
+    nk::DeviceGuard _restore_device;
     if (!ix) { nk::set_error("null index"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
     const uint64_t N = ix->mask_on ? ix->mask_alive : ix->rows();  // rows that can be returned
@@ -887,18 +908,50 @@ int nk_search(NkIndex *ix, const float *queries_host, uint32_t Q, uint32_t k, ui
     }
 
     if (single) {
+        // Results and status words come back through ONE pinned staging buffer: three short DMA copies and a single stream
+        // synchronisation (pageable cudaMemcpyAsync targets cost a driver-side staging round trip each).
         NkShard *s = live[0];
         NK_CUDA_OK(cudaSetDevice(s->device));
+        const size_t rbytes = (size_t)Q * ke * 4, need = 2 * rbytes + sizeof(int) * nk::NK_FLAG_WORDS;
+        if (s->h_res_bytes < need) {
+            if (s->h_res) cudaFreeHost(s->h_res);
+            s->h_res = nullptr; s->h_res_bytes = 0;
+            NK_CUDA_OK(cudaMallocHost((void **)&s->h_res, need + need / 4));
+            s->h_res_bytes = need + need / 4;
+        }
+        int *hflags = reinterpret_cast<int *>(s->h_res + 2 * rbytes);
         for (int pass = 0; pass < 2; ++pass) {
-            NK_CUDA_OK(cudaMemcpy2DAsync(out_idx, (size_t)k * 4, s->ws.out_idx, (size_t)ke * 4, (size_t)ke * 4, Q,
-                                         cudaMemcpyDeviceToHost, s->stream));
-            NK_CUDA_OK(cudaMemcpy2DAsync(out_score, (size_t)k * 4, s->ws.out_score, (size_t)ke * 4, (size_t)ke * 4, Q,
-                                         cudaMemcpyDeviceToHost, s->stream));
+            NK_CUDA_OK(cudaMemcpyAsync(s->h_res, s->ws.out_idx, rbytes, cudaMemcpyDeviceToHost, s->stream));
+            NK_CUDA_OK(cudaMemcpyAsync(s->h_res + rbytes, s->ws.out_score, rbytes, cudaMemcpyDeviceToHost, s->stream));
+            NK_CUDA_OK(cudaMemcpyAsync(hflags, s->ws.flags, sizeof(int) * nk::NK_FLAG_WORDS, cudaMemcpyDeviceToHost, s->stream));
+            NK_CUDA_OK(cudaStreamSynchronize(s->stream));
             ix->stats.bytes_d2h += (uint64_t)Q * ke * 8;
-            if (pass == 1) { NK_CUDA_OK(cudaStreamSynchronize(s->stream)); break; }
-            const int r = finish_deferred(ix, *s);  // synchronises; > 0: a retry stage rewrote the results
-            if (r < 0) return -1;
-            if (r == 0) break;
+            if (hflags[nk::FLAG_FATAL]) {
+                cudaMemsetAsync(s->ws.flags, 0, sizeof(int), s->stream);
+                nk::set_error("internal: candidate buffer overflow (flag=%d)", hflags[nk::FLAG_FATAL]);
+                return -1;
+            }
+            if (pass == 0 && s->last_filter && s->last_args.defer_tail && (hflags[nk::FLAG_RETRY] || hflags[nk::FLAG_OVERFLOW])) {
+                // a filter stage overflowed (near-ties, NaN rows): queue the retry / exact stages now and read again
+                NK_RANGE_PUSH("nk:retry-tail");
+                const int rc = nk::scan_tensor_filter_tail(s->di, s->last_args, s->ws, s->last_out_keys, &ix->stats.kernel_launches);
+                NK_RANGE_POP();
+                if (rc) return -1;
+                continue;
+            }
+            break;
+        }
+        s->last_filter = false;
+        const uint32_t *hi = reinterpret_cast<const uint32_t *>(s->h_res);
+        const float *hs = reinterpret_cast<const float *>(s->h_res + rbytes);
+        if (ke == k) {
+            memcpy(out_idx, hi, rbytes);
+            memcpy(out_score, hs, rbytes);
+        } else {
+            for (uint32_t q = 0; q < Q; ++q) {
+                memcpy(out_idx + (size_t)q * k, hi + (size_t)q * ke, (size_t)ke * 4);
+                memcpy(out_score + (size_t)q * k, hs + (size_t)q * ke, (size_t)ke * 4);
+            }
         }
         return (int)ke;
     }
@@ -959,6 +1012,7 @@ static int single_shard(NkIndex *ix, NkShard **out) {
 
 int nk_search_keys_device(NkIndex *ix, const float *queries_dev, uint32_t Q, uint32_t k, uint64_t *out_keys_dev,
                           void *stream) {
+    nk::DeviceGuard _restore_device;
     NkShard *s;
     if (single_shard(ix, &s)) return -1;
     if (k == 0 || Q == 0) return 0;
@@ -979,6 +1033,7 @@ int nk_search_keys_device(NkIndex *ix, const float *queries_dev, uint32_t Q, uin
 
 int nk_search_device(NkIndex *ix, const float *queries_dev, uint32_t Q, uint32_t k, uint32_t *out_idx_dev,
                      float *out_score_dev, void *stream) {
+    nk::DeviceGuard _restore_device;
     NkShard *s;
     if (single_shard(ix, &s)) return -1;
     if (k == 0 || Q == 0) return 0;
@@ -1003,6 +1058,7 @@ int nk_search_device(NkIndex *ix, const float *queries_dev, uint32_t Q, uint32_t
 // for `stream` (NULL = the index's own streams), reads and clears the sticky status word of every shard, and returns 0 or -1
 // with the message nk_search would have given.  Call it wherever the caller synchronises anyway.
 int nk_index_status(NkIndex *ix, void *stream) {
+    nk::DeviceGuard _restore_device;
     if (!ix) { nk::set_error("null index"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
     int bad = 0;
@@ -1025,6 +1081,7 @@ int nk_index_status(NkIndex *ix, void *stream) {
 // nothing.)
 int nk_merge_keys_device(int device_id, const uint64_t *keys_dev, uint32_t n_lists, uint32_t Q, uint32_t k, int metric,
                          uint32_t *out_idx_dev, float *out_score_dev, void *stream) {
+    nk::DeviceGuard _restore_device;
     if (k == 0 || Q == 0 || n_lists == 0) return 0;
     if (!keys_dev || !out_idx_dev || !out_score_dev) { nk::set_error("null argument"); return -1; }
     if (device_id < 0 || device_id >= 64) { nk::set_error("bad device id %d", device_id); return -1; }
@@ -1041,6 +1098,7 @@ int nk_merge_keys_device(int device_id, const uint64_t *keys_dev, uint32_t n_lis
 
 int nk_score_subset(NkIndex *ix, const float *query_host, const uint32_t *rows_host, uint32_t n_subset, uint32_t k,
                     uint32_t *out_idx, float *out_score) {
+    nk::DeviceGuard _restore_device;
     NkShard *s;
     if (single_shard(ix, &s)) return -1;
     if (n_subset == 0 || k == 0) return 0;
@@ -1105,6 +1163,7 @@ int nk_score_subset(NkIndex *ix, const float *query_host, const uint32_t *rows_h
 // queries — read in place from HBM, 8192 at a time — and k = 1.  Ties go to the lowest centroid index (strict < / >
 // in kmeans.go:470-476,529-534).
 int nk_index_assign_nearest(NkIndex *ix, const float *centroids_host, uint32_t K, int metric, int32_t *assign_io, uint64_t *changed) {
+    nk::DeviceGuard _restore_device;
     if (!ix || !centroids_host || !assign_io) { nk::set_error("null argument"); return -1; }
     if (ix->dtype != NK_DTYPE_F32) { nk::set_error("nk_index_assign_nearest: fp32 index required"); return -1; }
     if (K == 0) { nk::set_error("nk_index_assign_nearest: K must be >= 1"); return -1; }
@@ -1168,6 +1227,7 @@ int nk_index_assign_nearest(NkIndex *ix, const float *centroids_host, uint32_t K
 // Update step (kmeans.go:585-618): centroid c <- float32(mean in float64 of the rows assigned to c); clusters without
 // members keep their previous position.  Rows with an assignment outside [0, K) are ignored.
 int nk_index_cluster_means(NkIndex *ix, const int32_t *assign_host, uint32_t K, float *centroids_io, uint32_t *counts_out) {
+    nk::DeviceGuard _restore_device;
     if (!ix || !assign_host || !centroids_io) { nk::set_error("null argument"); return -1; }
     if (ix->dtype != NK_DTYPE_F32) { nk::set_error("nk_index_cluster_means: fp32 index required"); return -1; }
     if (K == 0) return 0;
@@ -1214,6 +1274,7 @@ int nk_index_cluster_means(NkIndex *ix, const int32_t *assign_host, uint32_t K, 
 // Rows are chunk embeddings; group_of_row[r] = the node row r belongs to (ids in [0, n_groups)).  Stays set until a
 // row-count changing mutation (like the row mask, whose bits are positions).
 int nk_index_set_row_groups(NkIndex *ix, const uint32_t *group_of_row, uint64_t n_rows, uint32_t n_groups) {
+    nk::DeviceGuard _restore_device;
     if (!ix) { nk::set_error("null index"); return -1; }
     std::lock_guard<std::mutex> lk(ix->mu);
     if (!group_of_row) {
@@ -1241,6 +1302,7 @@ int nk_index_set_row_groups(NkIndex *ix, const uint32_t *group_of_row, uint64_t 
 // reference keeps a node only if bestScore >= 0, call_vector.go:243).  Exact fp32 scores, no over-select loop: one pass
 // with a per-node atomic max (segment-max), one top-k over the node keys.  Returns the number of nodes found (<= k).
 int nk_search_groups(NkIndex *ix, const float *query_host, uint32_t k, uint32_t *out_group, uint32_t *out_row, float *out_score) {
+    nk::DeviceGuard _restore_device;
     NkShard *s;
     if (single_shard(ix, &s)) return -1;
     if (k == 0 || s->n == 0) return 0;
@@ -1284,6 +1346,7 @@ int nk_search_groups(NkIndex *ix, const float *query_host, uint32_t k, uint32_t 
 // rank must make the same sequence of calls.  out_*_dev: [Q x k] on this rank's device, identical on every rank.
 int nk_search_sharded_device(NkIndex *ix, NkComm *comm, const float *queries_dev, uint32_t Q, uint32_t k, uint32_t *out_idx_dev,
                              float *out_score_dev, void *stream) {
+    nk::DeviceGuard _restore_device;
     NkShard *s;
     if (single_shard(ix, &s)) return -1;
     if (!comm) { nk::set_error("null communicator"); return -1; }
@@ -1302,6 +1365,7 @@ int nk_search_sharded_device(NkIndex *ix, NkComm *comm, const float *queries_dev
 
 int nk_fill_uniform_device(int device_id, float *out_dev, uint64_t n_rows, uint32_t dim, uint64_t seed,
                            uint64_t row_base, void *stream) {
+    nk::DeviceGuard _restore_device;
     NK_CUDA_OK(cudaSetDevice(device_id));
     return nk::fill_uniform(out_dev, NK_DTYPE_F32, n_rows, dim, seed, row_base, (cudaStream_t)stream);
 }

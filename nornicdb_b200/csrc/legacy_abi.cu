@@ -40,6 +40,7 @@ int cuda_get_device_count(void) {
 int cuda_is_available(void) { return cuda_get_device_count() > 0 ? 1 : 0; }
 
 CudaDevice *cuda_create_device(int device_id) {
+    nk::DeviceGuard _restore_device;
     NK_CUDA_OK_PTR(cudaSetDevice(device_id));
     CudaDevice *dev = new (std::nothrow) CudaDevice();
     if (!dev) {
@@ -63,6 +64,7 @@ CudaDevice *cuda_create_device(int device_id) {
 }
 
 void cuda_release_device(CudaDevice *dev) {
+    nk::DeviceGuard _restore_device;
     if (!dev) return;
     cudaSetDevice(dev->device_id);
     if (dev->stream) {
@@ -104,6 +106,7 @@ int cuda_device_compute_capability(int device_id) {
 }
 
 CudaBuffer *cuda_create_buffer(CudaDevice *dev, float *host_data, size_t count, int memory_type) {
+    nk::DeviceGuard _restore_device;
     if (dev) NK_CUDA_OK_PTR(cudaSetDevice(dev->device_id));
     CudaBuffer *buf = (CudaBuffer *)malloc(sizeof(CudaBuffer));
     if (!buf) {
@@ -139,6 +142,7 @@ CudaBuffer *cuda_create_buffer(CudaDevice *dev, float *host_data, size_t count, 
 }
 
 void cuda_release_buffer(CudaBuffer *buf) {
+    nk::DeviceGuard _restore_device;
     if (!buf) return;
     if (buf->data) {
         if (buf->memory_type == 0) cudaFree(buf->data);
@@ -151,6 +155,7 @@ void *cuda_buffer_data(CudaBuffer *buf) { return buf ? buf->data : nullptr; }
 size_t cuda_buffer_size(CudaBuffer *buf) { return buf ? buf->size : 0; }
 
 int cuda_buffer_copy_to_host(CudaBuffer *buf, float *host_data, size_t count) {
+    nk::DeviceGuard _restore_device;
     if (!buf || !host_data) return -1;
     size_t copy_size = count * sizeof(float);
     if (copy_size > buf->size) copy_size = buf->size;
@@ -181,6 +186,7 @@ static int check_buf(const CudaBuffer *b, size_t floats, const char *what) {
 }
 
 int cuda_compute_norms(CudaDevice *dev, CudaBuffer *vectors, CudaBuffer *norms, unsigned int n, unsigned int dims) {
+    nk::DeviceGuard _restore_device;
     if (!dev) { nk::set_error("invalid device"); return -1; }
     if (check_buf(vectors, (size_t)n * dims, "vectors") || check_buf(norms, n, "norms")) return -1;
     std::lock_guard<std::mutex> lk(dev->mu);
@@ -191,6 +197,7 @@ int cuda_compute_norms(CudaDevice *dev, CudaBuffer *vectors, CudaBuffer *norms, 
 }
 
 int cuda_normalize_vectors(CudaDevice *dev, CudaBuffer *vectors, unsigned int n, unsigned int dims) {
+    nk::DeviceGuard _restore_device;
     if (!dev) { nk::set_error("invalid device"); return -1; }
     if (check_buf(vectors, (size_t)n * dims, "vectors")) return -1;
     std::lock_guard<std::mutex> lk(dev->mu);
@@ -202,6 +209,7 @@ int cuda_normalize_vectors(CudaDevice *dev, CudaBuffer *vectors, unsigned int n,
 
 int cuda_cosine_similarity(CudaDevice *dev, CudaBuffer *embeddings, CudaBuffer *query, CudaBuffer *scores,
                            unsigned int n, unsigned int dims, int normalized) {
+    nk::DeviceGuard _restore_device;
     if (!dev) { nk::set_error("invalid device"); return -1; }
     if (check_buf(embeddings, (size_t)n * dims, "embeddings") || check_buf(query, dims, "query") ||
         check_buf(scores, n, "scores"))
@@ -215,6 +223,7 @@ int cuda_cosine_similarity(CudaDevice *dev, CudaBuffer *embeddings, CudaBuffer *
 
 int cuda_topk(CudaDevice *dev, CudaBuffer *scores, unsigned int *out_indices, float *out_scores, unsigned int n,
               unsigned int k) {
+    nk::DeviceGuard _restore_device;
     if (k == 0 || n == 0) return 0;  // cuda_bridge.go:329-331
     if (k > n) k = n;                // cuda_bridge.go:332-334
     if (!dev) { nk::set_error("invalid device"); return -1; }

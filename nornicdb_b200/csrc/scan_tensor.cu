@@ -116,7 +116,7 @@ __device__ __forceinline__ float warp_exact_score(const void *rows, int dtype, s
         const float4 *x4 = reinterpret_cast<const float4 *>(static_cast<const float *>(rows) + local * dim);
 #pragma unroll 8
         for (uint32_t j = lane; j < dim / 4; j += 32) acc4(__ldg(x4 + j), q4[j]);
-    } else {  // fp16 rows, dim % 8 == 0: 8 halves per 128-bit load
+    } else if (dtype == NK_DTYPE_F16) {  // fp16 rows, dim % 8 == 0: 8 halves per 128-bit load
         const uint4 *x8 = reinterpret_cast<const uint4 *>(static_cast<const __half *>(rows) + local * dim);
 #pragma unroll 4
         for (uint32_t j = lane; j < dim / 8; j += 32) {
@@ -125,6 +125,14 @@ __device__ __forceinline__ float warp_exact_score(const void *rows, int dtype, s
             const float2 f2 = __half22float2(*reinterpret_cast<const __half2 *>(&w.z)), f3 = __half22float2(*reinterpret_cast<const __half2 *>(&w.w));
             acc4(make_float4(f0.x, f0.y, f1.x, f1.y), q4[2 * j]);
             acc4(make_float4(f2.x, f2.y, f3.x, f3.y), q4[2 * j + 1]);
+        }
+    } else {  // bf16 rows: widening is a 16-bit shift
+        const uint4 *x8 = reinterpret_cast<const uint4 *>(static_cast<const uint16_t *>(rows) + local * dim);
+#pragma unroll 4
+        for (uint32_t j = lane; j < dim / 8; j += 32) {
+            const uint4 w = __ldg(x8 + j);
+            acc4(make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16), __uint_as_float(w.y & 0xffff0000u)), q4[2 * j]);
+            acc4(make_float4(__uint_as_float(w.z << 16), __uint_as_float(w.z & 0xffff0000u), __uint_as_float(w.w << 16), __uint_as_float(w.w & 0xffff0000u)), q4[2 * j + 1]);
         }
     }
 #pragma unroll
@@ -154,7 +162,7 @@ __device__ __forceinline__ float warp_exact_score(const void *rows, int dtype, s
 //     score, so the scan starts with a real threshold instead of buffering every (row, query) pair of its first two
 //     tiles and pruning 64-128 full buffers per CTA (~25 us per launch, the largest fixed cost of a small-shard search).
 // ---------------------------------------------------------------------------------------------------
-constexpr int PREP_THREADS = 256;
+constexpr int PREP_THREADS = 1024;  // 32 warps: the sample scoring is latency-bound (one 4 KB row per warp at a time)
 struct PrepParams {
     const float *q;
     uint32_t Q, dim, dimpad;
@@ -266,7 +274,7 @@ __global__ void __launch_bounds__(PREP_THREADS) filter_prep_kernel(PrepParams p)
             const float sc = warp_exact_score(p.rows, p.dtype, (size_t)r, p.dim, qs, t, p.metric, lane, &xx);
             // lower bound of the real-valued score: the fp32 summation allowance the filters use (acc_c |x||q|)
             float lo = sc - (p.metric == NK_METRIC_COSINE ? p.acc_c : p.metric == NK_METRIC_DOT ? p.acc_c * sqrtf(xx * t) : p.acc_c * -sc);
-            if (lo == lo && lo > -INFINITY) key = (uint64_t)ord_bits(lo);
+            if (lo == lo && lo > -INFINITY && lo < INFINITY) key = (uint64_t)ord_bits(lo);
         }
         if (lane == 0) skeys[i] = key;
     }
@@ -682,9 +690,10 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
 // The LAST CTA to finish does the stage bookkeeping that used to be two more launches: it turns the stage's overflow
 // flag into the retry marker and, if a retry is due, wipes the shared thresholds and list fills.
 // ---------------------------------------------------------------------------------------------------
-constexpr int FINISH_THREADS = 256;
+constexpr int FINISH_THREADS = 1024;  // one CTA per query has an SM to itself: 32 warps for the list passes and the re-scoring
 constexpr int FINISH_CAP = 4096;
 constexpr int FINISH_WIN = FINISH_CAP - 256;  // list entries per round; the carried best k (<= 192) fits in the rest
+constexpr uint32_t ORD_POS_INF = 0xFF800000u;  // ord_bits(+inf): the bound of a row whose score is undecidable (NaN)
 struct FinishParams {
     const void *rows;        // corpus shard (fp32, or fp16 for the fp16 tensor path)
     int dtype;
@@ -740,28 +749,37 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
     // k-th largest bound by radix select over the score bits that actually vary (8 bits per pass, smem histogram; the
     // list is read from L2), then everything inside the margin below it is gathered for exact re-scoring.
     __shared__ int hist[256];
-    __shared__ uint32_t s_prefix, s_red[2][FINISH_THREADS / 32];
+    __shared__ uint32_t s_prefix, s_red[3][FINISH_THREADS / 32];
     __shared__ int s_krem;
+    // Rows with an undecidable score (NaN -> bound +inf) are always kept but say nothing about the k-th best score: the
+    // threshold comes from the k-th largest FINITE bound = the (k + n_inf)-th largest overall.
     uint32_t umax = 0u, umin = 0xffffffffu;
+    int ninf = 0;
     for (int i = tid; i < n; i += FINISH_THREADS) {
         const uint32_t hi = (uint32_t)(__ldcg(list + i) >> 32);
         umax = max(umax, hi);
         umin = min(umin, hi);
+        ninf += hi >= ORD_POS_INF ? 1 : 0;
     }
     umax = __reduce_max_sync(0xffffffffu, umax);
     umin = __reduce_min_sync(0xffffffffu, umin);
-    if (lane == 0) { s_red[0][warp] = umax; s_red[1][warp] = umin; }
-    if (tid == 0) { s_count = 0; s_krem = (int)p.k; }
+    ninf = __reduce_add_sync(0xffffffffu, ninf);
+    if (lane == 0) { s_red[0][warp] = umax; s_red[1][warp] = umin; s_red[2][warp] = (uint32_t)ninf; }
+    if (tid == 0) s_count = 0;
     __syncthreads();
+    ninf = 0;
 #pragma unroll
-    for (int w = 0; w < FINISH_THREADS / 32; ++w) { umax = max(umax, s_red[0][w]); umin = min(umin, s_red[1][w]); }
-    uint64_t thr_key = 1ull;  // fewer than k entries: keep them all
-    if (n >= (int)p.k) {
+    for (int w = 0; w < FINISH_THREADS / 32; ++w) { umax = max(umax, s_red[0][w]); umin = min(umin, s_red[1][w]); ninf += (int)s_red[2][w]; }
+    const int k_eff = (int)p.k + ninf;
+    if (tid == 0) s_krem = k_eff;
+    uint64_t thr_key = 1ull;  // fewer than k decidable entries: keep them all
+    if (n >= k_eff) {
         int rem = 32 - __clz(umax ^ umin);  // low bits in which the bounds differ (0: all equal)
         if (tid == 0) s_prefix = rem >= 32 ? 0u : (umax >> rem) << rem;
+        __syncthreads();
         while (rem > 0) {
             const int w = rem < 8 ? rem : 8, shift = rem - w;
-            hist[tid] = 0;  // FINISH_THREADS == 256
+            if (tid < 256) hist[tid] = 0;
             __syncthreads();
             const uint32_t prefix = s_prefix;
             for (int i = tid; i < n; i += FINISH_THREADS) {
@@ -858,6 +876,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
     if (!s_last) return;
     __threadfence();
     const int ovf = atomicOr(p.flags + FLAG_OVERFLOW, 0);
+    if (tid == 0 && ovf) atomicOr(p.flags + FLAG_OVF_BITS, ovf);
     if (p.mark_retry) {
         if (ovf)
             for (uint32_t i = tid; i < p.state_words; i += FINISH_THREADS) p.state[i] = 0u;
@@ -1060,12 +1079,14 @@ static int make_filter_plan(const DeviceInfo &di, const ScanArgs &a, Workspace &
     f.big = shadow_pass_supported(di, a);
     f.stage2 = f.big && a.dtype == NK_DTYPE_F32 && tc_common_ok(di, a);
     f.can_exact_tc = scan_tensor_supported(di, a);  // euclidean / 16-bit rows have no 3xTF32 twin: overflow -> CUDA-core scan
-    if (f.big && f.k_emit < 128) f.k_emit = 128;  // BF16 margins are ~3x wider: more rows per CTA sit inside them
+    // 16-bit margins are ~6x wider than TF32's and clustered corpora put hundreds of rows per CTA inside them: the 16-bit
+    // kernel has 1024-slot buffers and emits up to 512 entries per (CTA, query) (the finish step re-scores in rounds)
+    if (f.big) f.k_emit = a.k <= 160 ? 512u : (uint32_t)(P_SHADOW - ROWS);
     f.dimpad = f.big ? a.shadow_dimpad : (a.dim + 63) / 64 * 64;
     const bool need_f32q = a.dtype == NK_DTYPE_F32;  // hi / lo arrays only serve passes over fp32 rows
     const size_t qaux_floats = (need_f32q ? (size_t)2 * f.Qpad * a.dim : 0) + (size_t)3 * f.QA;
     if (ws_reserve((void **)&ws.qaux, &ws.qaux_bytes, qaux_floats * 4 + (f.big ? (size_t)f.Qpad * f.dimpad * 2 : 0))) return -1;
-    if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)f.grid * QT_MAX * P * 8)) return -1;
+    if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)f.grid * QT_MAX * (f.big ? P_SHADOW : P) * 8)) return -1;
     if (ws_reserve((void **)&ws.partial, &ws.partial_bytes, (size_t)a.Q * f.grid * f.k_emit * 8)) return -1;
     if (ws_reserve((void **)&ws.keys2, &ws.keys2_bytes, (size_t)f.QA * 8)) return -1;  // gtau[] + gcount[]
     f.qhi = need_f32q ? ws.qaux : nullptr;
@@ -1077,14 +1098,14 @@ static int make_filter_plan(const DeviceInfo &di, const ScanArgs &a, Workspace &
     f.max_groups = (uint32_t)tc_env_int("NK_TC_QGROUPS", 4);
     // G query groups leave each CTA 1/G of the grid for its queries, i.e. G times the rows — and G times the rows inside
     // the BF16 margin — per (CTA, query) buffer: large k keeps fewer groups so that k + margin rows stay inside k_emit
-    f.max_groups_shadow = a.k <= 32 ? 4u : a.k <= 64 ? 2u : 1u;
+    f.max_groups_shadow = a.k <= 128 ? 4u : a.k <= 160 ? 2u : 1u;
     if (f.max_groups_shadow > f.max_groups) f.max_groups_shadow = f.max_groups;
     // Sampled initial threshold: single-pass batches on shards with enough tiles per CTA for the flood tiles to matter.
     // (Large batches re-score the sample once per query — more L2 traffic than the flood tiles cost.)
     f.sample = 0;
     if (tc_env_int("NK_TAU_SAMPLE", 1) && a.Q <= 128 && a.n >= 4096) {
-        f.sample = next_pow2(16 * a.k);
-        if (f.sample < 256) f.sample = 256;
+        f.sample = next_pow2(8 * a.k);  // k-th best of the sample = top k/S of the shard: ~8-12% of the rows pass at first
+        if (f.sample < 128) f.sample = 128;
         if (f.sample > 2048) f.sample = 2048;
     }
     f.fsmem = (size_t)FINISH_CAP * 16 + (size_t)a.dim * 4;
@@ -1125,7 +1146,8 @@ static int scan_tensor_exact(const DeviceInfo &di, const ScanArgs &a, Workspace 
         if (launch_pass<3, 64>(di, a, ws, t, launches)) return -1;
     }
     if (count_main && a.ev_end) NK_CUDA_OK(cudaEventRecord(a.ev_end, a.stream));
-    if (merge_keys(ws.partial, grid, a.k, (size_t)grid * a.k, a.Q, a.k, out_keys, a.stream, only_if)) return -1;
+    // fold the per-CTA lists and, when the caller wants them, write the decoded (index, score) arrays in the same launch
+    if (merge_keys(ws.partial, grid, a.k, (size_t)grid * a.k, a.Q, a.k, out_keys, a.stream, only_if, 0, a.out_idx, a.out_score, a.metric)) return -1;
     if (launches) ++*launches;
     if (count_main) tc_print_prof(a.stream, num_tiles, grid, (a.dim + BK - 1) / BK);
     return 0;
@@ -1137,10 +1159,7 @@ int scan_tensor(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t
         set_error("tensor path: unsupported shape");
         return -1;
     }
-    if (scan_tensor_exact(di, a, ws, out_keys, launches, nullptr, true, true)) return -1;
-    if (a.out_idx && decode_keys(out_keys, a.Q, a.k, a.metric, a.out_idx, a.out_score, a.stream)) return -1;
-    if (a.out_idx && launches) ++*launches;
-    return 0;
+    return scan_tensor_exact(di, a, ws, out_keys, launches, nullptr, true, true);
 }
 
 // TF32 passes over queries [qfirst, Q): 128 query columns per MMA while more than 64 queries remain (twice the queries per
@@ -1202,14 +1221,9 @@ int scan_tensor_filter_tail(const DeviceInfo &di, const ScanArgs &a, Workspace &
         if (scan_tensor_exact(di, b, ws, out_keys, launches, ws.flags + FLAG_OVERFLOW, false, false)) return -1;
     } else {  // euclidean / large k / 16-bit rows: the CUDA-core scan is the exact twin
         b.only_if = ws.flags + FLAG_OVERFLOW;
-        b.out_idx = nullptr; b.out_score = nullptr;
         if (scan_simt(di, b, ws, out_keys, launches)) return -1;
     }
-    if (a.out_idx) {
-        if (decode_keys(out_keys, a.Q, a.k, a.metric, a.out_idx, a.out_score, a.stream, ws.flags + FLAG_OVERFLOW)) return -1;
-        if (launches) ++*launches;
-    }
-    return 0;
+    return 0;  // (both exact twins write the decoded arrays from their merge launch)
 }
 
 // Filter mode: prep -> 16-bit (or 1xTF32) scan with rigorous margins -> finish (select by upper bound, exact fp32

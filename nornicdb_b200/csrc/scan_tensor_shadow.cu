@@ -42,6 +42,8 @@ constexpr int ASTAGES = 4;
 constexpr int A_BYTES = ROWS * 128;       // 32 KB
 constexpr int MAX_BSTAGES = 8;
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 8, EPI_NT = EPI_WARPS * 32;
+constexpr int PB = tc::P_SHADOW;          // candidate buffer slots per (CTA, query)
+constexpr int PRUNE_LANE = PB / 32;       // keys per lane of a warp prune
 
 template <int QT> struct Cfg {
     static constexpr int B_BYTES = QT * 128;
@@ -276,8 +278,8 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
         const uint32_t m = (uint32_t)(warp - EPI_WARP0) >> 2, quad = warp & 3, ewarp = warp - EPI_WARP0;
         const uint32_t lane_base = (quad * 32u) << 16;
         const uint32_t rt = m * 128 + quad * 32 + lane;  // row within the tile
-        uint64_t *my_cand = p.cand + (size_t)blockIdx.x * QT * P;
-        const int prune_at = P - ROWS;
+        uint64_t *my_cand = p.cand + (size_t)blockIdx.x * QT * PB;
+        const int prune_at = PB - ROWS;
         const bool cosine = p.metric == NK_METRIC_COSINE, euclid = p.metric == NK_METRIC_EUCLIDEAN;
         uint32_t it = 0;
         for (uint32_t tile = sub; tile < num_tiles; tile += sgrid, ++it) {
@@ -345,7 +347,7 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
                             float sc = fmaf(__uint_as_float(c < 32 ? v0[c & 31] : v1[c & 31]), mul, fmaf(ra, sh.qa[qi], rb * sh.qb[qi]));
                             if (euclid) { const float qn = sh.qn[qi]; sc -= EUC_KEEP * fmaf(qn, qn, x2); }
                             if (sc != sc) sc = INFINITY;
-                            my_cand[(size_t)qi * P + slot] = (alive && sc >= p.min_score) ? make_key(sc, grow) : 0ull;  // 0 = empty slot
+                            my_cand[(size_t)qi * PB + slot] = (alive && sc >= p.min_score) ? make_key(sc, grow) : 0ull;  // 0 = empty slot
                         }
                     }
                     if (rt == 0 && chunk == 0)
@@ -387,7 +389,7 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
                         if (sc != sc) sc = INFINITY;  // undecidable here: keep it, the exact rescoring judges
                         if (sc >= sh.tau[qi]) {
                             int pos = atomicAdd(&sh.cnt[qi], 1);
-                            if (pos < P) my_cand[(size_t)qi * P + pos] = make_key(sc, (uint32_t)(p.row_base + row));
+                            if (pos < PB) my_cand[(size_t)qi * PB + pos] = make_key(sc, (uint32_t)(p.row_base + row));
                             else atomicExch(p.flags, 1);
                         }
                     }
@@ -402,7 +404,7 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
                     float floor_tau = p.min_score;
                     const uint32_t gt = __ldcg(p.gtau + q0 + qi);
                     if (gt) floor_tau = fmaxf(floor_tau, ord_to_float(gt));
-                    warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, true, margin2, prune_at, floor_tau,
+                    warp_prune<PRUNE_LANE>(my_cand + (size_t)qi * PB, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, true, margin2, prune_at, floor_tau,
                                    nullptr, p.flags + FLAG_OVERFLOW);
                     // everything inside the margin must fit below prune_at, or the next tile could overflow the buffer
                     if (lane == 0 && sh.cnt[qi] >= prune_at) atomicOr(p.flags + FLAG_OVERFLOW, 1);
@@ -420,7 +422,7 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
     __syncthreads();
     {
         const bool cosine = p.metric == NK_METRIC_COSINE;
-        uint64_t *my_cand = p.cand + (size_t)blockIdx.x * QT * P;
+        uint64_t *my_cand = p.cand + (size_t)blockIdx.x * QT * PB;
         for (uint32_t qi = warp; qi < nq; qi += NTHREADS / 32) {
             const float margin2 = bf16_margin2(p.metric, __uint_as_float(sh.max_ra), cosine ? 1.0f : __uint_as_float(sh.max_rb),
                                                __uint_as_float(sh.maxxx), sh.qa[qi], sh.qb[qi], sh.qn[qi]);
@@ -433,11 +435,11 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
                 const float t = fmaxf(sh.tau[qi], floor_tau);
                 uint64_t thr = t > -INFINITY ? (uint64_t)ord_bits(t) << 32 : 1ull;
                 if (thr == 0ull) thr = 1ull;
-                warp_emit_above(my_cand + (size_t)qi * P, sh.cnt[qi], thr, lane, p.partial + (size_t)(q0 + qi) * p.list_cap,
+                warp_emit_above(my_cand + (size_t)qi * PB, sh.cnt[qi], thr, lane, p.partial + (size_t)(q0 + qi) * p.list_cap,
                                 (int)p.list_cap, p.gcount + q0 + qi);
                 continue;
             }
-            warp_prune<16>(my_cand + (size_t)qi * P, &sh.cnt[qi], &sh.tau[qi], p.k, lane,
+            warp_prune<PRUNE_LANE>(my_cand + (size_t)qi * PB, &sh.cnt[qi], &sh.tau[qi], p.k, lane,
                            p.partial + (size_t)(q0 + qi) * p.list_cap, (int)p.list_cap, true, margin2,
                            (int)p.k_emit, floor_tau, p.gcount + q0 + qi, p.flags + FLAG_OVERFLOW);
             if (lane == 0 && sh.cnt[qi] >= (int)p.k_emit && (int)p.k_emit > (int)p.k) atomicOr(p.flags + FLAG_OVERFLOW, 2);

@@ -20,6 +20,8 @@ enum {
     FLAG_LONGEST = 7,     // longest shared list of this search (diagnostics)
     FLAG_N_RETRY = 8,     // cumulative: searches whose first (BF16) stage overflowed
     FLAG_N_EXACT = 9,     // cumulative: searches that fell through to the exact kernels
+    FLAG_OVF_BITS = 10,   // cumulative OR of the overflow reasons seen: 1 margin buffer could not be pruned below prune_at,
+                          // 2 emission cut at k_emit, 8 non-finite bound / margin
     NK_FLAG_WORDS = 16
 };
 namespace tc {
@@ -28,7 +30,8 @@ constexpr int BK = 32;           // floats per corpus K-slab = one 128-byte swiz
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_THREADS = 128;
 constexpr int EPI_BAR = 1;
-constexpr int P = 512;           // candidate buffer capacity per (CTA, query): warp_prune<16>
+constexpr int P = 512;           // candidate buffer capacity per (CTA, query) of the TF32 kernels: warp_prune<16>
+constexpr int P_SHADOW = 1024;   // ... of the 16-bit kernel (wider margins, 4 query groups at k = 100): warp_prune<32>
 constexpr int QT_BIG = 256;      // padding of the per-query arrays (a CTA reads up to 128 entries past the last query)
 constexpr float EUC_EPS = 4e-6f;  // fp32 rounding of |x|^2 + |q|^2 in the euclidean upper bound
 constexpr float EUC_KEEP = 1.0f - EUC_EPS;

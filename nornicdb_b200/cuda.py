@@ -209,6 +209,11 @@ class Device:  # cuda_bridge.go:407-415
         if lib.nk_index_attach_device_rows(ix, embeddings.DataPtr(), n) != 0:
             lib.nk_index_release(ix)
             raise ErrKernelExecution(f"cuda: kernel execution failed: {_lib.last_error()}")
+        # The rows are final by the time the reference searches them (syncToCUDA = NewBuffer + NormalizeVectors, then
+        # Search, gpu.go:2073-2118): build the BF16 shadow now so the drop-in route runs the fast filter path.
+        if lib.nk_index_refresh_shadow(ix) != 0:
+            lib.nk_index_release(ix)
+            raise ErrKernelExecution(f"cuda: kernel execution failed: {_lib.last_error()}")
         embeddings._index, embeddings._index_key = ix, key
         return ix
 

@@ -149,7 +149,7 @@ class KnnIndex:
     def debug_counters(self) -> dict:
         out = (C.c_uint64 * 4)()
         _check(self.lib.nk_index_debug_counters(self.ptr, out), "nk_index_debug_counters")
-        return {"bf16_stage_retries": int(out[0]), "exact_stage_runs": int(out[1]), "longest_list": int(out[2])}
+        return {"bf16_stage_retries": int(out[0]), "exact_stage_runs": int(out[1]), "longest_list": int(out[2]), "overflow_bits": int(out[3])}
 
     def filter_dump(self, queries, which: str = "shadow") -> Tuple[np.ndarray, np.ndarray]:
         """Tests only: (estimate, bound) arrays [rows x Q] of the filter kernel `which` ("shadow" | "filter")."""

@@ -62,6 +62,35 @@ class FakeKnnIndex:
     def set_path(self, path):
         pass
 
+    def set_metric(self, metric):
+        self.metric = metric
+
+    def set_min_score(self, v):
+        self._floor = None if v is None else float(v)
+
+    def set_row_groups(self, group_of_row, n_groups=None):
+        self._groups = None if group_of_row is None else np.asarray(group_of_row, dtype=np.int64).reshape(-1).copy()
+
+    def search_groups(self, query, k):
+        q = np.asarray(query, dtype=np.float32).reshape(1, -1)
+        kept = np.arange(len(self)) if self._mask is None else np.nonzero(self._mask)[0]
+        if len(kept) == 0:
+            return np.empty(0, np.uint32), np.empty(0, np.uint32), np.empty(0, np.float32)
+        idx, sc = oracle.knn_exact64(self._rows[kept], q, len(kept), self.metric)
+        floor = getattr(self, "_floor", None)
+        out, seen = [], set()
+        for r, s in zip(kept[idx[0]].tolist(), sc[0].tolist()):
+            if floor is not None and (s > floor if self.metric == "euclidean" else s < floor):
+                continue
+            g = int(self._groups[r])
+            if g in seen:
+                continue
+            seen.add(g)
+            out.append((g, r, s))
+            if len(out) == k:
+                break
+        return (np.array([o[0] for o in out], np.uint32), np.array([o[1] for o in out], np.uint32), np.array([o[2] for o in out], np.float32))
+
     def last_path(self):
         return "fake"
 
@@ -81,7 +110,13 @@ class FakeKnnIndex:
         if ke <= 0 or q.shape[0] == 0:
             return np.empty((q.shape[0], 0), np.uint32), np.empty((q.shape[0], 0), np.float32)
         idx, sc = oracle.knn_exact64(rows[kept], q, ke, self.metric)
-        return kept[idx].astype(np.uint32), sc.astype(np.float32)
+        gi, gs = kept[idx].astype(np.uint32), sc.astype(np.float32)
+        floor = getattr(self, "_floor", None)
+        if floor is not None:  # the device leaves 0xffffffff / 0 in slots below the score floor
+            bad = sc > floor if self.metric == "euclidean" else sc < floor
+            gi[bad] = 0xFFFFFFFF
+            gs[bad] = 0.0
+        return gi, gs
 
     def score_subset(self, query, rows, k=None):
         q = np.ascontiguousarray(np.asarray(query, dtype=np.float32).reshape(-1))

@@ -75,3 +75,51 @@ def test_query_nodes_best_of_chunks(knn_lib, kats, oracle_mod):
     # nodes whose best score is negative are dropped (call_vector.go:240-242)
     res = query_nodes([("pos", [[1, 0]]), ("neg", [[-1, 0]])], [1, 0], 5, "cosine")
     assert [r[0] for r in res] == ["pos"]
+
+
+def test_node_vector_index_resident_labels_and_batch_add(knn_lib, oracle_mod):
+    """queryNodes over a RESIDENT chunk corpus: label filter = row bitmask, best-of-chunks = device segment-max, the
+    `bestScore >= 0` rule = the kernels' score floor; VectorIndex.AddBatch = one device append."""
+    from nornicdb_b200.vector_index import NodeVectorIndex, VectorIndex
+    rng = np.random.default_rng(4)
+    d, n_nodes = 48, 700
+    chunks = oracle_mod.fill_uniform(2500, d, 21)
+    nodes, labels, at = [], [], 0
+    for i in range(n_nodes):
+        c = int(rng.integers(1, 6))
+        nodes.append((f"n{i}", chunks[at:at + c]))
+        labels.append(("Doc",) if i % 3 else ("Doc", "Memory"))
+        at += c
+    q = oracle_mod.fill_uniform(1, d, 22)[0]
+    for sim in ("cosine", "dot", "euclidean"):
+        nv = NodeVectorIndex(d, sim)
+        nv.Load(nodes, labels)
+        for label in ("", "Memory"):
+            got = nv.Query(q, 12, label)
+            ref = []
+            for (nid, cs), ls in zip(nodes, labels):
+                if label and label not in ls:
+                    continue
+                x = cs.astype(np.float64)
+                if sim == "cosine":
+                    best = max(oracle_mod.vec_cosine64(c, q) for c in cs)
+                elif sim == "dot":
+                    best = float((x @ q.astype(np.float64)).max())
+                else:
+                    best = float((1.0 / (1.0 + np.sqrt(((x - q) ** 2).sum(1)))).max())
+                if best >= 0.0:
+                    ref.append((nid, best))
+            ref.sort(key=lambda t: -t[1])
+            assert [g[0] for g in got] == [r[0] for r in ref[:12]], (sim, label)
+            assert np.allclose([g[1] for g in got], [r[1] for r in ref[:12]], rtol=1e-4, atol=1e-6)
+        nv.Release()
+    # AddBatch == Add in a loop
+    rows = oracle_mod.fill_uniform(500, d, 23)
+    a, b = VectorIndex(d), VectorIndex(d)
+    for i, v in enumerate(rows):
+        a.Add(f"d{i}", v)
+    b.AddBatch([f"d{i}" for i in range(500)], rows)
+    b.AddBatch(["d3", "new"], [rows[7], rows[9]])  # update in place + one fresh id
+    a.Add("d3", rows[7]); a.Add("new", rows[9])
+    assert a.Search(q, 20, 0.1) == b.Search(q, 20, 0.1)
+    a.Release(); b.Release()
