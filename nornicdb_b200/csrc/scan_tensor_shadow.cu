@@ -279,7 +279,12 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
         const uint32_t lane_base = (quad * 32u) << 16;
         const uint32_t rt = m * 128 + quad * 32 + lane;  // row within the tile
         uint64_t *my_cand = p.cand + (size_t)blockIdx.x * QT * PB;
+        // capacity rule: a buffer must be prunable below PB - ROWS, or the next tile could overflow it.  Prunes are TRIGGERED
+        // much earlier (hidden behind the MMAs): an early, tight threshold keeps the buffers short, so the emission at the
+        // end of the launch needs no selection and the finish step reads short lists (small shards: 26 tiles per CTA at
+        // N = 1M would otherwise never prune at all).
         const int prune_at = PB - ROWS;
+        const int prune_trigger = min(prune_at, max(256, 4 * (int)p.k));
         const bool cosine = p.metric == NK_METRIC_COSINE, euclid = p.metric == NK_METRIC_EUCLIDEAN;
         uint32_t it = 0;
         for (uint32_t tile = sub; tile < num_tiles; tile += sgrid, ++it) {
@@ -398,7 +403,7 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
             // prune any buffer that could overflow during the next tile (8 warps, different queries concurrently)
             group_sync(EPI_BAR, EPI_NT);  // every push of this tile is visible
             for (uint32_t qi = ewarp; qi < nq; qi += EPI_WARPS)
-                if (sh.cnt[qi] > prune_at) {
+                if (sh.cnt[qi] > prune_trigger) {
                     const float margin2 = bf16_margin2(p.metric, __uint_as_float(sh.max_ra), cosine ? 1.0f : __uint_as_float(sh.max_rb),
                                                        __uint_as_float(sh.maxxx), sh.qa[qi], sh.qb[qi], sh.qn[qi]);
                     float floor_tau = p.min_score;
