@@ -2,20 +2,39 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "kernels.cuh"
 
 namespace nk {
 
+// Thread-local message (the reference's buffer is one racy process-global, cuda_bridge.go:21-33) with a process-wide
+// fallback: cgo may move a goroutine to another OS thread between the failing call and cuda_get_last_error(), and a thread
+// that has no message of its own then reads the most recent one of the process instead of an empty string.
 static thread_local char g_err[512] = {0};
+static thread_local char g_ret[512] = {0};
+static std::mutex g_last_mu;
+static char g_last[512] = {0};
 
 void set_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+    std::lock_guard<std::mutex> lk(g_last_mu);
+    memcpy(g_last, g_err, sizeof(g_last));
 }
-const char *get_error() { return g_err; }
-void clear_error() { g_err[0] = 0; }
+const char *get_error() {
+    if (g_err[0]) return g_err;
+    std::lock_guard<std::mutex> lk(g_last_mu);
+    memcpy(g_ret, g_last, sizeof(g_ret));  // a stable per-thread copy: the caller reads it after the lock is gone
+    return g_ret;
+}
+void clear_error() {
+    g_err[0] = 0;
+    std::lock_guard<std::mutex> lk(g_last_mu);
+    g_last[0] = 0;
+}
 
 int query_device_info(int device_id, DeviceInfo *out) {
     cudaDeviceProp prop;

@@ -125,6 +125,9 @@ public:
         std::lock_guard<std::mutex> lk(mu_);
         if (cuda_normalize_vectors(ptr_, vectors.ptr_, n, dimensions) != 0)
             throw ErrKernelExecution("cuda: kernel execution failed: " + takeError());
+        // the buffer was rewritten: the 16-bit image of a cached index must follow
+        if (vectors.index_ && nk_index_refresh_shadow(vectors.index_) != 0)
+            throw ErrKernelExecution(std::string("cuda: kernel execution failed: ") + nk_last_error());
     }
     void CosineSimilarity(Buffer &embeddings, Buffer &query, Buffer &scores, uint32_t n, uint32_t dimensions, bool normalized) {  // :600-618
         std::lock_guard<std::mutex> lk(mu_);
@@ -157,7 +160,10 @@ public:
             if (embeddings.index_) nk_index_release(embeddings.index_);
             int dev = id_;
             embeddings.index_ = nk_index_create(&dev, 1, dimensions, NK_DTYPE_F32, (int)metric);
-            if (!embeddings.index_ || nk_index_attach_device_rows(embeddings.index_, cuda_buffer_data(embeddings.ptr_), n) != 0)
+            // rows are final by the time they are searched (syncToCUDA = NewBuffer + NormalizeVectors, gpu.go:2073-2118):
+            // refresh_shadow gives the attached (caller-owned) rows the fast BF16 filter path
+            if (!embeddings.index_ || nk_index_attach_device_rows(embeddings.index_, cuda_buffer_data(embeddings.ptr_), n) != 0 ||
+                nk_index_refresh_shadow(embeddings.index_) != 0)
                 throw ErrKernelExecution(std::string("cuda: kernel execution failed: ") + nk_last_error());
             embeddings.index_n_ = n; embeddings.index_dim_ = dimensions; embeddings.index_metric_ = (int)metric;
         }
