@@ -1051,6 +1051,7 @@ static void tc_print_prof(cudaStream_t stream, uint32_t num_tiles, uint32_t grid
 // (device, args).  Deterministic, so the host-driven retry of nk_search can rebuild it after the fact.
 struct FilterPlan {
     uint32_t Qpad, QA, num_tiles, grid, k_emit, dimpad, sample;
+    bool pair;          // batches of >= 256 queries run on CTA pairs (scan_tensor_pair.cu)
     bool big;           // first stage = 16-bit pass (BF16 shadow of an fp32 shard, or an fp16 / bf16 corpus itself)
     bool stage2;        // the TF32 filter over the fp32 rows exists as the retry stage (fp32 shards with a shadow)
     bool can_exact_tc;  // exact stage = 3xTF32 kernel (else the CUDA-core scan)
@@ -1086,7 +1087,8 @@ static int make_filter_plan(const DeviceInfo &di, const ScanArgs &a, Workspace &
     const bool need_f32q = a.dtype == NK_DTYPE_F32;  // hi / lo arrays only serve passes over fp32 rows
     const size_t qaux_floats = (need_f32q ? (size_t)2 * f.Qpad * a.dim : 0) + (size_t)3 * f.QA;
     if (ws_reserve((void **)&ws.qaux, &ws.qaux_bytes, qaux_floats * 4 + (f.big ? (size_t)f.Qpad * f.dimpad * 2 : 0))) return -1;
-    if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)f.grid * QT_MAX * (f.big ? P_SHADOW : P) * 8)) return -1;
+    f.pair = f.big && a.Q >= 256 && pair_pass_supported(di, a, f.grid);
+    if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)f.grid * (f.pair ? 256 : QT_MAX) * (f.big ? P_SHADOW : P) * 8)) return -1;
     if (ws_reserve((void **)&ws.partial, &ws.partial_bytes, (size_t)a.Q * f.grid * f.k_emit * 8)) return -1;
     if (ws_reserve((void **)&ws.keys2, &ws.keys2_bytes, (size_t)f.QA * 8)) return -1;  // gtau[] + gcount[]
     f.qhi = need_f32q ? ws.qaux : nullptr;
@@ -1257,7 +1259,12 @@ int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
         ShadowPassArgs sp{};
         sp.grid = f.grid; sp.k_emit = f.k_emit; sp.dimpad = f.dimpad; sp.Qpad = f.Qpad; sp.q0 = q0;
         sp.qbf16 = f.qbf16; sp.qnorm = f.qnorm; sp.qa = f.qa; sp.qb = f.qb; sp.presampled = f.sample != 0;
-        if (left > 64) {
+        if (left >= 256 && f.pair) {
+            // large batches: CTA pairs, 256 query columns per MMA, two query blocks per launch sharing tiles through L2
+            sp.qgroups = (left >= 512 && f.grid >= 8) ? 2u : 1u;
+            sp.nq = left < 256u * sp.qgroups ? left / 256u * 256u : 256u * sp.qgroups;
+            if (launch_pair_pass(di, a, ws, sp, launches)) return -1;
+        } else if (left > 64) {
             uint32_t groups = 1;
             if (left > 3 * 128 && f.max_groups_shadow >= 4 && f.grid % 4 == 0 && f.grid >= 8) groups = 4;
             else if (left > 128 && f.max_groups_shadow >= 2 && f.grid % 2 == 0 && f.grid >= 4) groups = 2;

@@ -111,6 +111,9 @@ struct ShadowPassArgs {
 };
 int launch_shadow_pass(int qt, const DeviceInfo &di, const ScanArgs &a, Workspace &ws, const ShadowPassArgs &sp, uint64_t *launches);
 bool shadow_pass_supported(const DeviceInfo &di, const ScanArgs &a);
+// The same pass on CTA pairs (scan_tensor_pair.cu: tcgen05.mma.cta_group::2, 256 query columns): nq <= qgroups * 256
+bool pair_pass_supported(const DeviceInfo &di, const ScanArgs &a, uint32_t grid);
+int launch_pair_pass(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, const ShadowPassArgs &sp, uint64_t *launches);
 // stand-alone bf16 conversion of a query block (k-means assignment: centroids as "queries")
 int bf16_prep_queries(const ScanArgs &a, uint32_t Qpad, uint32_t dimpad, float acc_c, void *qbf16, float *qnorm, float *qa,
                       float *qb, uint64_t *launches);

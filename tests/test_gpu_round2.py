@@ -362,3 +362,35 @@ def test_exchange_across_gpus_in_one_process(knn_lib, oracle_mod):
     oi, os_ = oracle_mod.knn_exact64(rows, q, k, "cosine")
     for gi, gs in res:
         check_parity(rows, q, k, "cosine", gi, gs, oi, os_)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", ["cosine", "dot", "euclidean"])
+@pytest.mark.parametrize("Q,k", [(256, 10), (300, 10), (520, 100), (1024, 10)])
+def test_large_batches_on_cta_pairs(knn_lib, oracle_mod, metric, Q, k):
+    """Q >= 256: the 16-bit pass runs on CTA pairs (tcgen05.mma.cta_group::2, 256 query columns), the remainder on the
+    single-CTA kernels; results must match the fp64 oracle like every other path."""
+    n, d = 70_000, 128
+    rows = oracle_mod.fill_uniform(n, d, 101)
+    q = oracle_mod.fill_uniform(Q, d, 102)
+    ix = _index(rows, metric, path="shadow")
+    gi, gs = ix.search(q, k)
+    fl = ix.debug_flags()
+    ix.release()
+    assert fl[0] == 0
+    oi, os_ = oracle_mod.knn_exact64(rows, q, k, metric)
+    check_parity(rows, q, k, metric, gi, gs, oi, os_)
+
+
+def test_cta_pairs_fp16_corpus_and_ragged_rows(knn_lib, oracle_mod):
+    from nornicdb_b200.knn import KnnIndex
+    n, d, Q, k = 33_333, 256, 512, 10  # n not a multiple of the 256-row pair tile
+    rows = oracle_mod.fill_uniform(n, d, 103).astype(np.float16)
+    q = oracle_mod.fill_uniform(Q, d, 104)
+    ix = KnnIndex(d, metric="cosine", dtype="f16")
+    ix.upload(rows)
+    gi, gs = ix.search(q, k)
+    assert ix.last_path() == "shadow"
+    ix.release()
+    oi, os_ = oracle_mod.knn_exact64(rows, q, k, "cosine")
+    check_parity(rows, q, k, "cosine", gi, gs, oi, os_)
