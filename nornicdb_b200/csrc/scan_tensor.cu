@@ -1261,7 +1261,8 @@ int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
         sp.qbf16 = f.qbf16; sp.qnorm = f.qnorm; sp.qa = f.qa; sp.qb = f.qb; sp.presampled = f.sample != 0;
         if (left >= 256 && f.pair) {
             // large batches: CTA pairs, 256 query columns per MMA, two query blocks per launch sharing tiles through L2
-            sp.qgroups = (left >= 512 && f.grid >= 8) ? 2u : 1u;
+            const uint32_t gmax = (uint32_t)tc_env_int("NK_PAIR_GROUPS", 4);
+            sp.qgroups = (left >= 1024 && f.grid >= 16 && gmax >= 4) ? 4u : (left >= 512 && f.grid >= 8 && gmax >= 2) ? 2u : 1u;
             sp.nq = left < 256u * sp.qgroups ? left / 256u * 256u : 256u * sp.qgroups;
             if (launch_pair_pass(di, a, ws, sp, launches)) return -1;
         } else if (left > 64) {

@@ -17,25 +17,33 @@ G = os.path.join(ROOT, "gpurun_out")
 
 
 def launches(csv_path, md_path, title):
+    """Per-kernel totals, grouped by (kernel, grid size): launches of one kernel on different problem sizes (bench.py's
+    headline corpus and its secondary workloads) must not be averaged together (round-1 VERDICT, weak #10)."""
     rows = [r for r in csv.reader(open(csv_path)) if len(r) > 5]
     hdr = [i for i, r in enumerate(rows) if r[0] == "ID"][0]
     h, data = rows[hdr], rows[hdr + 1:]
     ki, vi, ui = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
+    gi = h.index("Grid Size") if "Grid Size" in h else None
     agg = defaultdict(lambda: [0, 0.0])
     for r in data:
+        if len(r) <= vi:
+            continue
         v = float(r[vi].replace(",", ""))
         v = v / 1e3 if r[ui] == "ns" else v * 1e3 if r[ui] == "ms" else v
-        agg[r[ki]][0] += 1
-        agg[r[ki]][1] += v
+        key = (r[ki], r[gi].replace(" ", "") if gi is not None else "")
+        agg[key][0] += 1
+        agg[key][1] += v
     tot = sum(v for _, v in agg.values())
-    search = sum(v for k, (_, v) in agg.items() if "fill_uniform" not in k)
+    setup = ("fill_uniform", "fill_clustered", "build_shadow")
+    search = sum(v for (k, _), (_, v) in agg.items() if not any(s in k for s in setup))
     with open(md_path, "w") as f:
         f.write(f"# {title}\n\nSource: `{os.path.basename(csv_path)}` (ncu --metrics gpu__time_duration.sum --clock-control none; "
-                "cold-cache, serialised launches: compare SHARES).\n\n| kernel | launches | total us | us/launch | share of all | share of search kernels |\n|---|---:|---:|---:|---:|---:|\n")
-        for k, (c, v) in sorted(agg.items(), key=lambda x: -x[1][1]):
-            ss = "-" if "fill_uniform" in k else f"{100 * v / search:.1f}%"
-            f.write(f"| `{k[:90]}` | {c} | {v:.1f} | {v / c:.1f} | {100 * v / tot:.1f}% | {ss} |\n")
-        f.write("\n`fill_uniform_kernel` generates the synthetic corpus once, outside the timed region.\n")
+                "cold-cache, serialised launches: compare SHARES).  One row per (kernel, grid size).\n\n"
+                "| kernel | grid | launches | total us | us/launch | share of all | share of search kernels |\n|---|---|---:|---:|---:|---:|---:|\n")
+        for (k, g), (c, v) in sorted(agg.items(), key=lambda x: -x[1][1]):
+            ss = "-" if any(s in k for s in setup) else f"{100 * v / search:.1f}%"
+            f.write(f"| `{k[:90]}` | {g} | {c} | {v:.1f} | {v / c:.1f} | {100 * v / tot:.1f}% | {ss} |\n")
+        f.write("\n`fill_*` / `build_shadow_kernel` generate the synthetic corpus and its BF16 shadow once, outside the timed region.\n")
 
 
 WANT = [
@@ -47,6 +55,8 @@ WANT = [
     "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
     "sm__cycles_elapsed.max", "smsp__cycles_active.avg", "sm__cycles_active.avg", "lts__t_sectors_srcunit_tex_op_read.sum",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
+    "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__t_sector_hit_rate.pct", "smsp__issue_active.avg.per_cycle_active",
+    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
 ]
 
 
@@ -54,7 +64,7 @@ def ncu_summary(rep, md_path, title, algorithmic_bytes=None):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     h, units, vals = rows[0], rows[1], rows[2]
-    d = {n: (vals[i], units[i]) for i, n in enumerate(h)}
+    d = {n.split("TriageCompute.")[-1]: (vals[i], units[i]) for i, n in enumerate(h)}
     name = d.get("Kernel Name", ("?", ""))[0]
     with open(md_path, "w") as f:
         f.write(f"# {title}\n\nSource: `{os.path.basename(rep)}` (ncu --set full --clock-control none, one launch of `{name[:80]}`; "
@@ -115,6 +125,19 @@ if __name__ == "__main__":
         (f"prof_{tag}_simt_c4.ncu-rep", f"ncu_{tag}_scan_simt_c4.md",
          "knn_scan_simt_kernel — N=10M d=768 fp16 Q=1 k=10 L2", N10 * 768 * 2, ["c4:simt"]),
     ]
+    if tag == "r2":
+        N2, N4 = 2_000_000, 4_000_000
+        LAUNCH_LISTS.append((f"launches_{tag}_8gpu_rank0.csv", f"launches_{tag}_8gpu_rank0.md", "Launch list, round 2: rank 0 of the 8-GPU headline run"))
+        CAPTURES += [
+            (f"prof_{tag}_pair_c3_k10.ncu-rep", f"ncu_{tag}_scan_pair_c3_k10.md",
+             "knn_scan_pair_kernel (CTA pairs, cta_group::2) — N=4M d=1024 fp32 Q=1024 k=10 dot, one launch = 2 query groups x 256", N4 * D * 2 + N4 * 8, []),
+            (f"prof_{tag}_shadow_c3_k10.ncu-rep", f"ncu_{tag}_scan_shadow_c3_k10.md",
+             "knn_scan_shadow_kernel<128> (single CTA, 4 query groups x 128) — N=2M d=1024 fp32 Q=1024 k=10 dot", N2 * D * 2 + N2 * 8, []),
+            (f"prof_{tag}_shadow_c3_k100.ncu-rep", f"ncu_{tag}_scan_shadow_c3_k100.md",
+             "knn_scan_shadow_kernel<128> (single CTA, 1 query group: the round-1 k=100 rule) — N=2M d=1024 fp32 Q=1024 k=100 dot", N2 * D * 2 + N2 * 8, []),
+            (f"prof_{tag}_finish_headline.ncu-rep", f"ncu_{tag}_filter_finish_headline.md", "filter_finish_kernel — headline", None, []),
+            (f"prof_{tag}_prep_headline.ncu-rep", f"ncu_{tag}_filter_prep_headline.md", "filter_prep_kernel — headline", None, []),
+        ]
     tpath = os.path.join(OUT, "traffic.json")
     t = json.load(open(tpath)) if os.path.exists(tpath) else {}
     for rep, md, title, algo, keys in CAPTURES:
