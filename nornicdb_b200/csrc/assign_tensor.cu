@@ -285,16 +285,16 @@ bool assign_tensor_supported(const DeviceInfo &di, uint32_t dim, uint32_t K, int
 // rows / shadow / norms: one shard (device pointers); centroids_dev: [K x dim] fp32 on the same device; assign_dev: [n].
 int assign_tensor(const DeviceInfo &di, const float *rows, const void *shadow, uint32_t dimpad, const float *xnorm2, const float *dnorm2,
                   uint32_t n, uint32_t dim, const float *centroids_dev, uint32_t K, int metric, uint32_t *assign_dev, cudaStream_t stream,
-                  uint64_t *launches) {
+                  uint64_t *launches, void **scratch, size_t *scratch_bytes) {
     using namespace asg;
     if (n == 0) return 0;
     const uint32_t nqb = (K + QT - 1) / QT, Kpad = nqb * QT;
     const float acc_c = (float)dim * 2.384185791015625e-7f + 4e-6f;
     // scratch: bf16 centroids [Kpad x dimpad], qn / qa / qb [Kpad], near-tie list (every row could be one)
-    unsigned char *buf = nullptr;
-    const size_t off_q = 0, off_f = (size_t)Kpad * dimpad * 2, off_amb = off_f + (size_t)3 * Kpad * 4;
+    const size_t off_q = 0, off_f = ((size_t)Kpad * dimpad * 2 + 255) & ~(size_t)255, off_amb = off_f + (((size_t)3 * Kpad * 4 + 255) & ~(size_t)255);
     const size_t total = off_amb + 4 + (size_t)n * 4 + (size_t)n * 16 + 64;
-    NK_CUDA_OK(cudaMalloc((void **)&buf, total));
+    if (ws_reserve(scratch, scratch_bytes, total)) return -1;  // grow-only, reused across calls
+    unsigned char *buf = static_cast<unsigned char *>(*scratch);
     float *qn = reinterpret_cast<float *>(buf + off_f), *qa = qn + Kpad, *qb = qa + Kpad;
     uint32_t *amb_count = reinterpret_cast<uint32_t *>(buf + off_amb);
     uint32_t *amb_rows = amb_count + 1;
@@ -326,7 +326,6 @@ int assign_tensor(const DeviceInfo &di, const float *rows, const void *shadow, u
         if (e != cudaSuccess) set_error("assign_tensor: %s", cudaGetErrorString(e));
     }
     cudaStreamSynchronize(stream);
-    cudaFree(buf);
     return rc;
 }
 

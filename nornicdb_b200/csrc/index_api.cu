@@ -28,7 +28,7 @@ bool shadow_pass_supported(const DeviceInfo &di, const ScanArgs &a);
 bool assign_tensor_supported(const DeviceInfo &di, uint32_t dim, uint32_t K, int metric);
 int assign_tensor(const DeviceInfo &di, const float *rows, const void *shadow, uint32_t dimpad, const float *xnorm2, const float *dnorm2,
                   uint32_t n, uint32_t dim, const float *centroids_dev, uint32_t K, int metric, uint32_t *assign_dev, cudaStream_t stream,
-                  uint64_t *launches);
+                  uint64_t *launches, void **scratch, size_t *scratch_bytes);
 int build_shadow(const float *rows, uint64_t first, uint64_t count, uint32_t dim, uint32_t dimpad, void *shadow, float *xnorm2,
                  float *dnorm2, cudaStream_t stream);
 }
@@ -1198,7 +1198,7 @@ int nk_index_assign_nearest(NkIndex *ix, const float *centroids_host, uint32_t K
         }
         if (rc == 0 && tensor) {
             rc = nk::assign_tensor(s.di, static_cast<const float *>(s.rows), s.shadow, ix->dimpad(), s.xnorm2, s.dnorm2, (uint32_t)s.n, ix->dim,
-                                   d_cen, K, metric, d_idx, s.stream, &ix->stats.kernel_launches);
+                                   d_cen, K, metric, d_idx, s.stream, &ix->stats.kernel_launches, &s.ws.sub_gather, &s.ws.sub_gather_bytes);
         }
         const uint64_t B = 8192;  // rows per fused search: amortises the ~12 fixed launches of a search over 8 scan launches
         for (uint64_t b = 0; rc == 0 && !tensor && b < s.n; b += B) {

@@ -265,6 +265,17 @@ __global__ void __launch_bounds__(SIMT_THREADS) knn_scan_simt_kernel(SimtParams 
     }
 
     // ---- emit this CTA's best k per query --------------------------------------------------------
+    if (p.P == 512) {
+        // k <= 255: one warp per query selects the best k of the (<= 512) buffered keys with the register radix select
+        // (~2 us) instead of a 45-stage block bitonic sort — on small shards (configs[0]: one interval per CTA) the
+        // emission sort WAS the scan time.  The list goes out unsorted; merge_keys sorts.
+        __syncthreads();
+        for (uint32_t qi = warp; qi < p.nq; qi += SIMT_WARPS) {
+            uint64_t *dst = p.partial + ((size_t)(p.q0 + qi) * gridDim.x + blockIdx.x) * p.k;
+            warp_prune<16>(my_cand + (size_t)qi * p.P, &s_cnt[qi], &s_tau[qi], p.k, lane, dst, (int)p.k, false, 0.0f, (int)p.k, p.min_score);
+        }
+        return;
+    }
 #pragma unroll 1
     for (uint32_t qi = 0; qi < p.nq; ++qi) {
         block_prune(my_cand + (size_t)qi * p.P, p.P, &s_cnt[qi], &s_tau[qi], p.k, sbuf, p.P);
@@ -375,6 +386,12 @@ int scan_simt(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *
             grid_used = (uint32_t)di.num_sms * (uint32_t)occ;
             if (grid_used > num_iv) grid_used = num_iv;
             if (grid_used > max_grid) grid_used = max_grid;
+            // small shards (a few intervals per CTA at most): keep grid * k within one 2048-wide merge round
+            if (num_iv <= (uint32_t)di.num_sms * 8 && (uint64_t)grid_used * a.k > 2048) {
+                uint32_t cap = 2048 / a.k;
+                if (cap < (uint32_t)di.num_sms) cap = (uint32_t)di.num_sms;
+                if (grid_used > cap) grid_used = cap;
+            }
             if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)grid_used * 8 * P * 8)) return -1;
             if (ws_reserve((void **)&ws.partial, &ws.partial_bytes, (size_t)a.Q * grid_used * a.k * 8)) return -1;
         }

@@ -1,5 +1,6 @@
 """bench.py's output contract, checked without a GPU: helpers import, every workload BASELINE.json names is defined, and
-the committed bench lines (profiles/bench_r1.jsonl, produced by bench.py on a B200) carry every key the driver reads."""
+the committed bench lines (profiles/bench_r1.jsonl, profiles/bench_r2.jsonl, produced by bench.py on B200 boxes) carry every
+key the driver reads — round 2 also the in-run parity check and the north_star grid."""
 import json
 import os
 
@@ -46,3 +47,34 @@ def test_committed_bench_lines_follow_the_contract():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["unit"] == "queries/s" and "sample" in cb
     for d in ref:
         assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["cpu_baseline"]["value"] == d["value"]
+
+
+def test_round2_bench_lines_carry_parity_check_and_grid():
+    lines = [json.loads(l) for l in open(os.path.join(ROOT, "profiles", "bench_r2.jsonl"))]
+    by = {d["run"]: d for d in lines}
+    for d in lines:
+        for key in REQUIRED + ["scan", "timing"]:
+            assert key in d, (d["run"], key)
+        assert "scan" not in d["config"]  # moved to the top level so the two arms' configs compare equal
+        pc = d.get("parity_check")
+        if pc is None:  # the NCCL-exchange comparison run was taken with --no-parity
+            assert "nccl" in d["run"], d["run"]
+            continue
+        # every returned score is recomputed (bounded at 4096 row read-backs per rank for the Q=1024, k=100 shape)
+        assert pc["ok"] is True and pc["scores_recomputed_fp64"] >= min(d["config"]["Q"] * d["config"]["k"], 4096 * d["n_gpus"]), (d["run"], pc)
+        assert d["e2e"]["value"] <= d["value"] * 1.02, d["run"]  # one clock per quantity: e2e never beats device-resident
+        r = d["roofline"]
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    one = by["default_1gpu"]
+    want = {"c3", "c3_k10", "q1", "k100", "headline_filter", "q1_simt", "headline_clustered", "c4", "c4_q64", "c2", "c1"}
+    assert want <= set(one["also"]), sorted(set(one["also"]))
+    for name, e in one["also"].items():
+        assert "error" not in e, (name, e)
+        assert e["ms_per_step"] > 0 and 0 < e["roofline_frac"] < 1.25 and e["bound"] in ("hbm", "tensor")
+    assert one["also"]["headline_clustered"]["filter_retries"]["first_stage_retry_rate"] <= 0.05  # the round-1 cliff
+    st = one["cpu_baseline"]["single_thread"]
+    assert st["cores"] == 1 and st["value"] > 0 and one["cpu_baseline"]["value"] >= st["value"] * 0.9
+    for name in ("headline_8gpu_peer", "c5_8gpu_peer"):
+        checks = " ".join(by[name]["parity_check"]["checks"])
+        assert "bit-identical to nk_index_create(devices=0..7) + nk_search" in checks, name
+    assert by["headline_8gpu_peer"]["exchange"].startswith("peer-memory")
