@@ -693,6 +693,7 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
 constexpr int FINISH_THREADS = 1024;  // one CTA per query has an SM to itself: 32 warps for the list passes and the re-scoring
 constexpr int FINISH_CAP = 4096;
 constexpr int FINISH_WIN = FINISH_CAP - 256;  // list entries per round; the carried best k (<= 192) fits in the rest
+constexpr int FINISH_HI = 16384;              // score words of the list cached in shared memory (longer lists: read from L2)
 constexpr uint32_t ORD_POS_INF = 0xFF800000u;  // ord_bits(+inf): the bound of a row whose score is undecidable (NaN)
 struct FinishParams {
     const void *rows;        // corpus shard (fp32, or fp16 for the fp16 tensor path)
@@ -720,9 +721,10 @@ struct FinishParams {
 
 __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *sb = reinterpret_cast<uint64_t *>(smem_raw);                      // FINISH_CAP bound keys
-    uint64_t *se = reinterpret_cast<uint64_t *>(smem_raw + FINISH_CAP * 8);     // FINISH_CAP exact keys
-    float *qs = reinterpret_cast<float *>(smem_raw + FINISH_CAP * 16);          // query
+    uint32_t *shi = reinterpret_cast<uint32_t *>(smem_raw);                                   // FINISH_HI score words of the list
+    uint64_t *sb = reinterpret_cast<uint64_t *>(smem_raw + FINISH_HI * 4);                    // FINISH_CAP bound keys
+    uint64_t *se = reinterpret_cast<uint64_t *>(smem_raw + FINISH_HI * 4 + FINISH_CAP * 8);   // FINISH_CAP exact keys
+    float *qs = reinterpret_cast<float *>(smem_raw + FINISH_HI * 4 + FINISH_CAP * 16);        // query
     __shared__ float s_qq;
     __shared__ int s_count, s_last;
     if (p.only_if && *p.only_if == 0) return;
@@ -732,6 +734,32 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
     int n = p.gcount[q];
     if (tid == 0) atomicMax(p.flags + FLAG_LONGEST, n);  // diagnostics: longest shared list of this search
     if (n > (int)p.list_cap) n = (int)p.list_cap;
+    const uint64_t *list = p.lists + (size_t)q * p.list_cap;
+    // ONE pass over the list (L2): the score words go to shared memory — every selection pass below reads them from there
+    // (the list was read five times from L2, each time a chain of dependent ~1 us loads: that, not the arithmetic, was the
+    // finish step's cost).  Four independent loads per thread per iteration.
+    const bool cached = n <= FINISH_HI;
+    uint32_t umax = 0u, umin = 0xffffffffu;
+    int ninf = 0;
+    for (int i0 = tid; i0 < n; i0 += 4 * FINISH_THREADS) {
+        uint32_t h[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * FINISH_THREADS;
+            h[u] = i < n ? (uint32_t)(__ldcg(list + i) >> 32) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * FINISH_THREADS;
+            if (i < n) {
+                if (cached) shi[i] = h[u];
+                umax = max(umax, h[u]);
+                umin = min(umin, h[u]);
+                ninf += h[u] >= ORD_POS_INF ? 1 : 0;
+            }
+        }
+    }
+    auto hi_at = [&](int i) -> uint32_t { return cached ? shi[i] : (uint32_t)(__ldcg(list + i) >> 32); };
     __syncthreads();
     if (warp == 0) {
         float a = 0.0f;
@@ -740,33 +768,23 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
         for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         if (lane == 0) s_qq = a;
     }
-    __syncthreads();
-    const float maxxx = __uint_as_float((unsigned int)p.flags[FLAG_MAXXX]);
-    const float margin2 = q < p.q_big ? bf16_margin2(p.metric, __uint_as_float((unsigned int)p.flags[FLAG_MAX_RA]),
-                                                     __uint_as_float((unsigned int)p.flags[FLAG_MAX_RB]), maxxx, p.qa[q], p.qb[q], p.qn[q])
-                                      : filter_margin2(p.metric, p.margin_c, maxxx, sqrtf(s_qq));
-    const uint64_t *list = p.lists + (size_t)q * p.list_cap;
-    // k-th largest bound by radix select over the score bits that actually vary (8 bits per pass, smem histogram; the
-    // list is read from L2), then everything inside the margin below it is gathered for exact re-scoring.
+    // k-th largest bound by radix select over the score bits that actually vary (8 bits per pass, smem histogram), then
+    // everything inside the margin below it is gathered for exact re-scoring.
     __shared__ int hist[256];
     __shared__ uint32_t s_prefix, s_red[3][FINISH_THREADS / 32];
     __shared__ int s_krem;
     // Rows with an undecidable score (NaN -> bound +inf) are always kept but say nothing about the k-th best score: the
     // threshold comes from the k-th largest FINITE bound = the (k + n_inf)-th largest overall.
-    uint32_t umax = 0u, umin = 0xffffffffu;
-    int ninf = 0;
-    for (int i = tid; i < n; i += FINISH_THREADS) {
-        const uint32_t hi = (uint32_t)(__ldcg(list + i) >> 32);
-        umax = max(umax, hi);
-        umin = min(umin, hi);
-        ninf += hi >= ORD_POS_INF ? 1 : 0;
-    }
     umax = __reduce_max_sync(0xffffffffu, umax);
     umin = __reduce_min_sync(0xffffffffu, umin);
     ninf = __reduce_add_sync(0xffffffffu, ninf);
     if (lane == 0) { s_red[0][warp] = umax; s_red[1][warp] = umin; s_red[2][warp] = (uint32_t)ninf; }
     if (tid == 0) s_count = 0;
     __syncthreads();
+    const float maxxx = __uint_as_float((unsigned int)p.flags[FLAG_MAXXX]);
+    const float margin2 = q < p.q_big ? bf16_margin2(p.metric, __uint_as_float((unsigned int)p.flags[FLAG_MAX_RA]),
+                                                     __uint_as_float((unsigned int)p.flags[FLAG_MAX_RB]), maxxx, p.qa[q], p.qb[q], p.qn[q])
+                                      : filter_margin2(p.metric, p.margin_c, maxxx, sqrtf(s_qq));
     ninf = 0;
 #pragma unroll
     for (int w = 0; w < FINISH_THREADS / 32; ++w) { umax = max(umax, s_red[0][w]); umin = min(umin, s_red[1][w]); ninf += (int)s_red[2][w]; }
@@ -783,7 +801,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
             __syncthreads();
             const uint32_t prefix = s_prefix;
             for (int i = tid; i < n; i += FINISH_THREADS) {
-                const uint32_t hi = (uint32_t)(__ldcg(list + i) >> 32);
+                const uint32_t hi = hi_at(i);
                 if (rem >= 32 || (hi >> rem) == (prefix >> rem)) atomicAdd(&hist[(hi >> shift) & ((1u << w) - 1u)], 1);
             }
             __syncthreads();
@@ -796,6 +814,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
                     loc[j] = dgt >= 0 ? hist[dgt] : 0;
                     sum += loc[j];
                 }
+                __syncwarp();  // every lane has read s_krem / hist before the owner lane rewrites s_krem below
                 int incl = sum;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -829,16 +848,27 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
             atomicOr(p.flags + FLAG_OVERFLOW, 8);
         }
     }
-    // ---- rounds: gather survivors of a window of the list, re-score them exactly, fold into the running best k
+    // ---- how many rows are inside the margin?  Almost always a few dozen: ONE gather + re-score round.  Only adversarial
+    // near-tie data (thousands of survivors) goes through the list in windows, the running best k carried over.
+    const uint32_t thr_hi = (uint32_t)(thr_key >> 32);  // keys >= thr_key  <=>  score word >= thr_hi (thr_key's low word is 0 or 1)
+    int mine = 0;
+    for (int i = tid; i < n; i += FINISH_THREADS) mine += hi_at(i) >= thr_hi ? 1 : 0;
+    mine = __reduce_add_sync(0xffffffffu, mine);
+    if (lane == 0 && mine) atomicAdd(&s_count, mine);
+    __syncthreads();
+    const int survivors = s_count;
+    const int win = survivors <= FINISH_WIN ? (n > 0 ? n : 1) : FINISH_WIN;  // whole list in one round when the survivors fit
     int carry = 0;
-    for (int w0 = 0; w0 < n || w0 == 0; w0 += FINISH_WIN) {
+    for (int w0 = 0; w0 < n || w0 == 0; w0 += win) {
         __syncthreads();
         if (tid == 0) s_count = 0;
         __syncthreads();
-        const int w1 = min(n, w0 + FINISH_WIN);
+        const int w1 = min(n, w0 + win);
         for (int i = w0 + tid; i < w1; i += FINISH_THREADS) {
-            const uint64_t key = __ldcg(list + i);
-            if (key >= thr_key) sb[atomicAdd(&s_count, 1)] = key;
+            if (hi_at(i) >= thr_hi) {  // the full key is fetched only for survivors
+                const uint64_t key = __ldcg(list + i);
+                if (key >= thr_key) sb[atomicAdd(&s_count, 1)] = key;
+            }
         }
         __syncthreads();
         const int count = s_count;  // <= FINISH_WIN
@@ -849,11 +879,24 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
             if (lane == 0) se[carry + i] = sc >= p.min_score ? make_key(sc, grow) : 0ull;
         }
         const int total = carry + count;
-        int P2 = 32;
-        while (P2 < total) P2 <<= 1;
         __syncthreads();
-        for (int i = total + tid; i < P2; i += FINISH_THREADS) se[i] = 0ull;
-        block_bitonic_sort_desc(se, P2);
+        if (total <= FINISH_THREADS) {
+            // small sets (the common case): rank by counting — one barrier instead of a 15-45 stage bitonic network
+            const uint64_t mykey = tid < total ? se[tid] : 0ull;
+            int rank = 0;
+            for (int j = 0; j < total; ++j) rank += se[j] > mykey ? 1 : 0;  // keys are unique (row in the low word) or 0
+            __syncthreads();
+            if (tid < total && mykey) se[rank] = mykey;
+            // dropped (0) keys: fill the tail behind the live ones
+            int live = __syncthreads_count(tid < total && mykey != 0ull);
+            for (int i = live + tid; i < total; i += FINISH_THREADS) se[i] = 0ull;
+            __syncthreads();
+        } else {
+            int P2 = 32;
+            while (P2 < total) P2 <<= 1;
+            for (int i = total + tid; i < P2; i += FINISH_THREADS) se[i] = 0ull;
+            block_bitonic_sort_desc(se, P2);
+        }
         carry = total < (int)p.k ? total : (int)p.k;
     }
     for (uint32_t i = tid; i < p.k; i += FINISH_THREADS) {
@@ -1110,7 +1153,7 @@ static int make_filter_plan(const DeviceInfo &di, const ScanArgs &a, Workspace &
         if (f.sample < 128) f.sample = 128;
         if (f.sample > 2048) f.sample = 2048;
     }
-    f.fsmem = (size_t)FINISH_CAP * 16 + (size_t)a.dim * 4;
+    f.fsmem = (size_t)FINISH_HI * 4 + (size_t)FINISH_CAP * 16 + (size_t)a.dim * 4;
     f.psmem = (size_t)((a.dim + 3) & ~3u) * 4 + (size_t)f.sample * 8;
     if (tc_ensure_smem(reinterpret_cast<const void *>(filter_finish_kernel), di.device_id, f.fsmem)) return -1;
     if (f.psmem > 48 * 1024 && tc_ensure_smem(reinterpret_cast<const void *>(filter_prep_kernel), di.device_id, f.psmem)) return -1;

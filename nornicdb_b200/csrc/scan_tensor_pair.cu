@@ -18,6 +18,10 @@
 // by tcgen05.commit ... multicast::cluster to both CTAs), accempty[b] (leader; 8 epilogue warps of EACH CTA arrive, the
 // peer's through the cluster shared window).
 //
+// Optional (NK_PAIR_CLUSTER = 2 | 4): a cluster of C pairs on the SAME query block and C consecutive row tiles.  The two
+// query half-slabs are then loaded ONCE per cluster and TMA-multicast to the C even / C odd CTAs (-25 % / -37 % of the L2->SM
+// operand traffic that bounds this kernel); a ring stage is released when all C pairs have consumed it.
+//
 // Algorithmic HBM bytes per launch: n * dimpad * 2 + 8 n (one launch serves up to 2 groups x 256 queries; sibling pairs of
 // the two groups stream the same tiles at the same pace and share them through L2).
 #include <cuda.h>
@@ -73,6 +77,21 @@ __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *m, uint64_t 
         ::"r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(cache_hint)
         : "memory");
 }
+// the same, multicast to every CTA of `cta_mask` (same smem offset in each; completion counted on each destination pair's leader)
+__device__ __forceinline__ void tma_load_2d_pair_mc(const CUtensorMap *m, uint64_t *bar_local, void *smem_dst, int32_t c0, int32_t c1,
+                                                    uint16_t cta_mask, uint64_t cache_hint) {
+    const uint32_t bar = ptx::smem_u32(bar_local) & PEER_MASK;
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5, %6;"
+        ::"r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask), "l"(cache_hint)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void mma_bf16_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -81,14 +100,14 @@ __device__ __forceinline__ void mma_bf16_ss_pair(uint32_t d_tmem, uint64_t a_des
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // arrives on the barrier at the same offset in BOTH CTAs of the pair once all MMAs issued so far have completed
-__device__ __forceinline__ void tc_commit_pair(uint64_t *bar_local) {
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar_local, uint16_t cta_mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(ptx::smem_u32(bar_local)), "h"((uint16_t)3) : "memory");
+                 ::"r"(ptx::smem_u32(bar_local)), "h"(cta_mask) : "memory");
 }
 // arrive on the LEADER's copy of a barrier from either CTA
-__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar_local) {
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar_local, uint32_t leader_rank) {
     uint32_t remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(remote) : "r"(ptx::smem_u32(bar_local)));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(ptx::smem_u32(bar_local)), "r"(leader_rank));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t *smem_result, uint32_t cols) {
@@ -100,7 +119,7 @@ __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols)
 }
 }  // namespace pr
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pr::NTHREADS, 1)
+__global__ void __launch_bounds__(pr::NTHREADS, 1)
 knn_scan_pair_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_q, tc::Params p) {
     using namespace pr;
     extern __shared__ unsigned char smem_dyn[];
@@ -108,12 +127,15 @@ knn_scan_pair_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_
     Shared &sh = *reinterpret_cast<Shared *>(smem_raw + (size_t)RING_BYTES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();  // cluster = C pairs (C = 1, 2 or 4)
+    const uint32_t rank = crank & 1u, C = csize >> 1, cpair = crank >> 1;
     const bool leader = rank == 0;
-    const uint32_t num_tiles = (p.n + 2 * ROWS_CTA - 1) / (2 * ROWS_CTA);
-    // query groups: pair c serves query block (c % G) over the tile subset (c / G); sibling pairs share tiles through L2
-    const uint32_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-    const uint32_t grp = pair % p.qgroups, sub = pair / p.qgroups, sgrid = npairs / p.qgroups;
+    const uint16_t pair_mask = (uint16_t)(3u << (crank & ~1u)), all_mask = (uint16_t)((1u << csize) - 1u);
+    // query groups: cluster c serves query block (c % G) over the cluster-tile subset (c / G); siblings share tiles through L2.
+    // A cluster-tile is C consecutive 256-row tiles, one per pair.
+    const uint32_t num_tiles = (p.n + 2 * ROWS_CTA * C - 1) / (2 * ROWS_CTA * C);
+    const uint32_t cl = blockIdx.x / csize, ncl = gridDim.x / csize;
+    const uint32_t grp = cl % p.qgroups, sub = cl / p.qgroups, sgrid = ncl / p.qgroups;
     const uint32_t q0 = p.q0 + grp * QT, qpad_off = p.qpad_off + grp * QT;
     const uint32_t nq = p.nq - grp * QT < (uint32_t)QT ? p.nq - grp * QT : (uint32_t)QT;
     const uint64_t a_policy = p.qgroups > 1 ? ptx::CACHE_EVICT_NORMAL : ptx::CACHE_EVICT_FIRST;
@@ -122,7 +144,7 @@ knn_scan_pair_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_rows);
         ptx::prefetch_tensormap(&map_q);
-        for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&sh.full[i], 1); ptx::mbar_init(&sh.empty[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { ptx::mbar_init(&sh.full[i], 1); ptx::mbar_init(&sh.empty[i], C); }  // every pair releases a stage
         for (int b = 0; b < 2; ++b) { ptx::mbar_init(&sh.accfull[b], 1); ptx::mbar_init(&sh.accempty[b], 2 * EPI_WARPS); }
         sh.maxxx = 0u; sh.max_ra = 0u; sh.max_rb = 0u;
         ptx::fence_barrier_init();
@@ -152,8 +174,17 @@ knn_scan_pair_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_
                 if (ptx::elect_one_sync()) {
                     unsigned char *st = smem_raw + (size_t)s * STAGE_BYTES;
                     if (leader) ptx::mbar_arrive_expect_tx(&sh.full[s], 2 * STAGE_BYTES);  // both CTAs' bytes land on this barrier
-                    tma_load_2d_pair(&map_rows, &sh.full[s], st, (int32_t)(j * BKB), (int32_t)(tile * 2 * ROWS_CTA + rank * ROWS_CTA), a_policy);
-                    tma_load_2d_pair(&map_q, &sh.full[s], st + A_BYTES, (int32_t)(j * BKB), (int32_t)(qpad_off + rank * QH), ptx::CACHE_EVICT_LAST);
+                    tma_load_2d_pair(&map_rows, &sh.full[s], st, (int32_t)(j * BKB),
+                                     (int32_t)((tile * C + cpair) * 2 * ROWS_CTA + rank * ROWS_CTA), a_policy);
+                    if (C == 1) {
+                        tma_load_2d_pair(&map_q, &sh.full[s], st + A_BYTES, (int32_t)(j * BKB), (int32_t)(qpad_off + rank * QH), ptx::CACHE_EVICT_LAST);
+                    } else if (cpair == 0) {
+                        // one L2 read per query half-slab per cluster: multicast to the C even (rank 0) / odd (rank 1) CTAs
+                        uint16_t mask = 0;
+                        for (uint32_t c = 0; c < C; ++c) mask |= (uint16_t)(1u << (2 * c + rank));
+                        tma_load_2d_pair_mc(&map_q, &sh.full[s], st + A_BYTES, (int32_t)(j * BKB), (int32_t)(qpad_off + rank * QH), mask,
+                                            ptx::CACHE_EVICT_LAST);
+                    }
                 }
                 __syncwarp();
             }
@@ -175,8 +206,8 @@ knn_scan_pair_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_
                     const uint32_t d = tmem + buf * QT;
 #pragma unroll
                     for (uint32_t kk = 0; kk < 4; ++kk) mma_bf16_ss_pair(d, adesc + kk * 2, bdesc + kk * 2, idesc, (j | kk) != 0);
-                    tc_commit_pair(&sh.empty[s]);
-                    if (j + 1 == nslab) tc_commit_pair(&sh.accfull[buf]);
+                    tc_commit_pair(&sh.empty[s], all_mask);            // this pair is done with stage s (every CTA of the cluster counts C)
+                    if (j + 1 == nslab) tc_commit_pair(&sh.accfull[buf], pair_mask);
                 }
                 __syncwarp();
             }
@@ -193,7 +224,7 @@ knn_scan_pair_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_
         uint32_t it = 0;
         for (uint32_t tile = sub; tile < num_tiles; tile += sgrid, ++it) {
             const uint32_t buf = it & 1;
-            const uint32_t row = tile * 2 * ROWS_CTA + rank * ROWS_CTA + rt;
+            const uint32_t row = (tile * C + cpair) * 2 * ROWS_CTA + rank * ROWS_CTA + rt;
             const bool alive = row < p.n && (!p.mask || ((__ldg(p.mask + (row >> 5)) >> (row & 31)) & 1u));
             const float x2 = row < p.n ? __ldg(p.xnorm2 + row) : 0.0f;
             const float xn = sqrtf(x2);
@@ -222,7 +253,7 @@ knn_scan_pair_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_
                 if (chunk == 1) {  // this warp's share of the accumulator is in registers: hand it back to the leader's issuer
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_leader(&sh.accempty[buf]);
+                    if (lane == 0) mbar_arrive_leader(&sh.accempty[buf], crank & ~1u);
                 }
                 if (it < (uint32_t)FLOOD_TILES && cb < nq) {
                     const uint32_t slot = it * ROWS_CTA + rt;
@@ -354,7 +385,11 @@ int launch_pair_pass(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, con
     if (!map_rows || !map_q) return -1;
     const size_t smem = (size_t)RING_BYTES + sizeof(Shared) + 1024;
     if (tc_ensure_smem(reinterpret_cast<const void *>(knn_scan_pair_kernel), di.device_id, smem)) return -1;
-    uint32_t grid = sp.grid / (2 * sp.qgroups) * (2 * sp.qgroups);  // whole pairs, the same number per query group
+    uint32_t C = (uint32_t)tc_env_int("NK_PAIR_CLUSTER", 1);  // pairs per cluster (query half-slabs multicast across them)
+    if (C != 2 && C != 4) C = 1;
+    const uint32_t unit = 2 * C * sp.qgroups;  // whole clusters, the same number per query group
+    uint32_t grid = sp.grid / unit * unit;
+    if (grid == 0) { C = 1; grid = sp.grid / (2 * sp.qgroups) * (2 * sp.qgroups); }
     tc::Params p{};
     p.n = a.n; p.dim = a.dim; p.nslab = sp.dimpad / BKB; p.row_base = a.row_base;
     p.q0 = sp.q0; p.nq = sp.nq; p.k = a.k; p.qpad_off = sp.q0; p.qgroups = sp.qgroups; p.list_cap = sp.grid * sp.k_emit;
@@ -363,7 +398,27 @@ int launch_pair_pass(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, con
     p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.mask = a.row_mask;
     p.gtau = reinterpret_cast<uint32_t *>(ws.keys2); p.gcount = reinterpret_cast<int *>(ws.keys2) + (sp.Qpad + QT_BIG);
     p.presampled = 0; p.min_score = a.min_score; p.op_f16 = a.dtype == NK_DTYPE_F16;
-    knn_scan_pair_kernel<<<grid, NTHREADS, smem, a.stream>>>(*map_rows, *map_q, p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = a.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2 * C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (C > 1) {
+        // a GPC may not fit as many clusters of 2C SMs as it has SMs: never launch more clusters than can be co-resident
+        // (the kernel is persistent: every CTA must be running for the cluster barriers to complete)
+        int max_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, knn_scan_pair_kernel, &cfg) == cudaSuccess && max_clusters > 0) {
+            uint32_t ncl = grid / (2 * C);
+            if ((uint32_t)max_clusters < ncl) ncl = (uint32_t)max_clusters / sp.qgroups * sp.qgroups;
+            if (ncl == 0) { set_error("pair kernel: no room for a cluster of %u CTAs", 2 * C); return -1; }
+            grid = ncl * 2 * C;
+            cfg.gridDim = dim3(grid);
+        } else {
+            cudaGetLastError();
+        }
+    }
+    NK_CUDA_OK(cudaLaunchKernelEx(&cfg, knn_scan_pair_kernel, *map_rows, *map_q, p));
     NK_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
     if (a.main_launches) ++*a.main_launches;
