@@ -266,23 +266,73 @@ __global__ void __launch_bounds__(PREP_THREADS) filter_prep_kernel(PrepParams p)
     // ---- sampled initial threshold
     if (p.sample == 0 || row >= p.Q) return;
     const uint32_t S = p.sample;  // power of two
-    for (uint32_t i = w; i < S; i += NW) {
-        uint64_t key = 0ull;
-        const uint64_t r = p.n >= S ? (uint64_t)i * p.n / S : i;
-        if (r < p.n && (!p.mask || ((__ldg(p.mask + (r >> 5)) >> (r & 31)) & 1u))) {
-            float xx;
-            const float sc = warp_exact_score(p.rows, p.dtype, (size_t)r, p.dim, qs, t, p.metric, lane, &xx);
-            // lower bound of the real-valued score: the fp32 summation allowance the filters use (acc_c |x||q|)
-            float lo = sc - (p.metric == NK_METRIC_COSINE ? p.acc_c : p.metric == NK_METRIC_DOT ? p.acc_c * sqrtf(xx * t) : p.acc_c * -sc);
-            if (lo == lo && lo > -INFINITY && lo < INFINITY) key = (uint64_t)ord_bits(lo);
+    auto sample_row = [&](uint32_t i) -> uint64_t { return p.n >= S ? (uint64_t)i * p.n / S : i; };
+    auto lower_key = [&](float sc, float xx) -> uint64_t {
+        // lower bound of the real-valued score: the fp32 summation allowance the filters use (acc_c |x||q|)
+        const float lo = sc - (p.metric == NK_METRIC_COSINE ? p.acc_c : p.metric == NK_METRIC_DOT ? p.acc_c * sqrtf(xx * t) : p.acc_c * -sc);
+        return (lo == lo && lo > -INFINITY && lo < INFINITY) ? (uint64_t)ord_bits(lo) : 0ull;
+    };
+    auto admissible = [&](uint64_t r) -> bool { return r < p.n && (!p.mask || ((__ldg(p.mask + (r >> 5)) >> (r & 31)) & 1u)); };
+    if (p.dtype == NK_DTYPE_F32 && p.metric != NK_METRIC_EUCLIDEAN) {
+        // two rows per warp at a time: both rows' 128-bit loads are in flight together (the scoring is latency-bound:
+        // one 4 KB row per warp per round trip)
+        const float4 *q4 = reinterpret_cast<const float4 *>(qs);
+        for (uint32_t i = 2 * w; i < S; i += 2 * NW) {
+            const uint64_t r0 = sample_row(i), r1 = sample_row(i + 1);
+            const bool ok0 = admissible(r0), ok1 = i + 1 < S && admissible(r1);
+            const float4 *x0 = reinterpret_cast<const float4 *>(static_cast<const float *>(p.rows) + (ok0 ? r0 : 0) * p.dim);
+            const float4 *x1 = reinterpret_cast<const float4 *>(static_cast<const float *>(p.rows) + (ok1 ? r1 : 0) * p.dim);
+            float d0 = 0.f, d1 = 0.f, n0 = 0.f, n1 = 0.f;
+#pragma unroll 4
+            for (uint32_t j = lane; j < p.dim / 4; j += 32) {
+                const float4 a = __ldg(x0 + j), b = __ldg(x1 + j), u = q4[j];
+                d0 = fmaf(a.x, u.x, d0); n0 = fmaf(a.x, a.x, n0); d0 = fmaf(a.y, u.y, d0); n0 = fmaf(a.y, a.y, n0);
+                d0 = fmaf(a.z, u.z, d0); n0 = fmaf(a.z, a.z, n0); d0 = fmaf(a.w, u.w, d0); n0 = fmaf(a.w, a.w, n0);
+                d1 = fmaf(b.x, u.x, d1); n1 = fmaf(b.x, b.x, n1); d1 = fmaf(b.y, u.y, d1); n1 = fmaf(b.y, b.y, n1);
+                d1 = fmaf(b.z, u.z, d1); n1 = fmaf(b.z, b.z, n1); d1 = fmaf(b.w, u.w, d1); n1 = fmaf(b.w, b.w, n1);
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                d0 += __shfl_xor_sync(0xffffffffu, d0, o); n0 += __shfl_xor_sync(0xffffffffu, n0, o);
+                d1 += __shfl_xor_sync(0xffffffffu, d1, o); n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+            }
+            if (lane == 0) {
+                float s0 = d0, s1 = d1;
+                if (p.metric == NK_METRIC_COSINE) {
+                    const float e0 = sqrtf(n0 * t), e1 = sqrtf(n1 * t);
+                    s0 = e0 > 0.0f ? d0 / e0 : 0.0f;
+                    s1 = e1 > 0.0f ? d1 / e1 : 0.0f;
+                }
+                skeys[i] = ok0 ? lower_key(s0, n0) : 0ull;
+                if (i + 1 < S) skeys[i + 1] = ok1 ? lower_key(s1, n1) : 0ull;
+            }
         }
-        if (lane == 0) skeys[i] = key;
+    } else {
+        for (uint32_t i = w; i < S; i += NW) {
+            uint64_t key = 0ull;
+            const uint64_t r = sample_row(i);
+            if (admissible(r)) {
+                float xx;
+                const float sc = warp_exact_score(p.rows, p.dtype, (size_t)r, p.dim, qs, t, p.metric, lane, &xx);
+                key = lower_key(sc, xx);
+            }
+            if (lane == 0) skeys[i] = key;
+        }
     }
-    block_bitonic_sort_desc(skeys, (int)S);  // starts with a __syncthreads
-    if (tid == 0 && p.k <= S) {
-        const uint64_t kth = skeys[p.k - 1];
-        if (kth) {  // at least k live sampled rows
-            const float tau0 = fmaxf(ord_to_float((uint32_t)kth), p.min_score);
+    __syncthreads();
+    // k-th largest of the S lower bounds by counting ranks (S <= 2048: one barrier instead of a bitonic network)
+    if (p.k > S) return;
+    for (uint32_t i = tid; i < S; i += PREP_THREADS) {
+        const uint64_t mine = skeys[i];
+        if (!mine) continue;
+        uint32_t greater = 0, equal_before = 0;
+        for (uint32_t j = 0; j < S; ++j) {
+            const uint64_t o = skeys[j];
+            greater += o > mine ? 1u : 0u;
+            equal_before += (o == mine && j < i) ? 1u : 0u;
+        }
+        if (greater + equal_before == p.k - 1) {  // exactly one entry holds rank k-1 (ties ordered by position)
+            const float tau0 = fmaxf(ord_to_float((uint32_t)mine), p.min_score);
             if (tau0 > -INFINITY) p.state[row] = ord_bits(tau0);
         }
     }
