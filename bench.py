@@ -21,8 +21,9 @@ inside the library on the launching stream.  `cpu_baseline` = the oracle's AVX2 
 pkg/simd brute force timed on this box's host cores, single-threaded (how the reference runs a query) and on all
 cores, on a bounded >= 1 GB sample (N=1, rank 0 only).  `parity_check` = an UNTIMED post-check of the results of
 this very run (planted neighbours, exact fp64 recomputation of every returned score, uniqueness / order, and for
-N > 1 bit-equality with the in-process multi-device search).  `also` (default N=1 line only) = the rest of the
-north_star grid measured by the same rules: configs[1..3], Q=1, k=100, the fp32-row scans and the clustered corpus."""
+N > 1 bit-equality with the in-process multi-device search).  `also` (default N=1 line) = the rest of the north_star grid
+measured by the same rules: configs[1..3], Q=1, k=100, the fp32-row scans and the clustered corpus; on the default 8-GPU
+line `also.c5` = configs[4] (N=100M, the one config that needs 8 GPUs), with its own parity_check."""
 from __future__ import annotations
 
 import argparse
@@ -784,6 +785,28 @@ def main():
             except Exception as e:
                 also[name] = {"error": str(e)}
         line["also"] = also
+    # ---- configs[4] under the same run (8 GPUs, default workload only): N=100M needs the 8-way row sharding, so this is the
+    # one north_star config that only exists at N=8 — measured and parity-checked here so that the driver's own 8-GPU
+    # record carries it.  51 GB of rows + 26 GB of shadow per GPU; ~15 s on top of the headline run.
+    if G >= 8 and args.workload == "headline" and not overridden and not args.no_also and args.path == "auto":
+        n5, d5, dt5, Q5, k5, m5, desc5 = WORKLOADS["c5"]
+        entry = {}
+        try:
+            ix.release()
+            ix = None
+            lo5, hi5 = shard_range(n5, G, rank)
+            ix = KnnIndex(d5, metric=m5, dtype=dt5, devices=(local_rank,))
+            ix.set_row_base(lo5)
+            ix.fill_uniform(hi5 - lo5, CORPUS_SEED)
+            r5 = measure(run, ix, hi5 - lo5, n5, d5, dt5, Q5, k5, m5, 5, 2, want_e2e=True)
+            entry = also_entry(r5, hi5 - lo5, d5, dt5, Q5, desc5, peak, peak_src, "c5")
+            entry["n_gpus"] = G
+            entry["rows_per_gpu"] = hi5 - lo5
+            if not args.no_parity:
+                entry["parity_check"] = parity_check(run, ix, lo5, hi5, n5, d5, dt5, Q5, k5, m5, r5)
+        except Exception as e:  # every rank takes the same path up to here; a failure must not lose the headline line
+            entry = {"error": str(e)}
+        line["also"] = {"c5": entry}
     if G == 1 and rank == 0 and not args.no_cpu_baseline:
         r = cpu_reference_run(N_total, dim, dtype, Q, k, metric, budget_s=18.0)
         line["cpu_baseline"] = {"value": r["value"], "unit": "queries/s", "cores": r["cores"], "kind": r["kind"],

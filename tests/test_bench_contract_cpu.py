@@ -78,3 +78,5 @@ def test_round2_bench_lines_carry_parity_check_and_grid():
         checks = " ".join(by[name]["parity_check"]["checks"])
         assert "bit-identical to nk_index_create(devices=0..7) + nk_search" in checks, name
     assert by["headline_8gpu_peer"]["exchange"].startswith("peer-memory")
+    c5 = by["default_8gpu"]["also"]["c5"]  # configs[4] rides on the default 8-GPU command
+    assert c5["parity_check"]["ok"] is True and c5["rows_per_gpu"] == 12_500_000 and c5["value"] > 0
