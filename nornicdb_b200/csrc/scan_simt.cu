@@ -257,7 +257,12 @@ __global__ void __launch_bounds__(SIMT_THREADS) knn_scan_simt_kernel(SimtParams 
 #pragma unroll
         for (int qi = 0; qi < QT; ++qi) need |= (s_cnt[qi] > prune_at ? 1u : 0u) << qi;
         __syncthreads();
-        if (need) {
+        if (need && p.P == 512) {
+            // k <= 255: warp w prunes query w with the register radix select (QT <= 8 queries, 8 warps: all in parallel, ~2 us)
+            if (warp < QT && (need & (1u << warp)))
+                warp_prune<16>(my_cand + (size_t)warp * p.P, &s_cnt[warp], &s_tau[warp], p.k, lane, nullptr, 0, false, 0.0f, (int)p.k, p.min_score);
+            __syncthreads();
+        } else if (need) {
 #pragma unroll 1
             for (int qi = 0; qi < QT; ++qi)
                 if (need & (1u << qi)) block_prune(my_cand + (size_t)qi * p.P, p.P, &s_cnt[qi], &s_tau[qi], p.k, sbuf, p.P);
