@@ -166,11 +166,26 @@ knn_scan_pair_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_
 
     if (warp == 0) {
         // ===================================== TMA producer: own A half + own B half ===================
-        uint32_t g = 0;
+        uint32_t g = 0, epoch = 0;
+        const bool lockstep = p.sync_every != 0 && p.qgroups > 1;
         for (uint32_t tile = sub; tile < num_tiles; tile += sgrid) {
             for (uint32_t j = 0; j < nslab; ++j, ++g) {
                 const uint32_t s = g % STAGES;
                 ptx::mbar_wait(&sh.empty[s], ((g / STAGES) & 1) ^ 1);
+                if (lockstep && (j % p.sync_every) == 0) {
+                    // sibling lockstep (experiment, NK_PAIR_SYNC): the producers of the G clusters that stream this tile
+                    // subset issue the slab together, so that their requests for the same corpus lines meet in L2
+                    if (lane == 0) {
+                        const uint32_t target = (epoch + 1) * csize * p.qgroups;
+                        atomicAdd(p.sync + sub, 1u);
+                        uint32_t v;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.sync + sub) : "memory");
+                        } while ((int32_t)(v - target) < 0);
+                    }
+                    ++epoch;
+                    __syncwarp();
+                }
                 if (ptx::elect_one_sync()) {
                     unsigned char *st = smem_raw + (size_t)s * STAGE_BYTES;
                     if (leader) ptx::mbar_arrive_expect_tx(&sh.full[s], 2 * STAGE_BYTES);  // both CTAs' bytes land on this barrier
@@ -398,6 +413,14 @@ int launch_pair_pass(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, con
     p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.mask = a.row_mask;
     p.gtau = reinterpret_cast<uint32_t *>(ws.keys2); p.gcount = reinterpret_cast<int *>(ws.keys2) + (sp.Qpad + QT_BIG);
     p.presampled = 0; p.min_score = a.min_score; p.op_f16 = a.dtype == NK_DTYPE_F16;
+    p.sync_every = (uint32_t)tc_env_int("NK_PAIR_SYNC", 0);
+    if (p.sync_every && sp.qgroups > 1) {
+        if (ws_reserve((void **)&ws.below, &ws.below_bytes, 1024)) return -1;  // (the big-k bound array doubles as the counter block)
+        NK_CUDA_OK(cudaMemsetAsync(ws.below, 0, 1024, a.stream));
+        p.sync = reinterpret_cast<uint32_t *>(ws.below);
+    } else {
+        p.sync_every = 0;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NTHREADS); cfg.dynamicSmemBytes = smem; cfg.stream = a.stream;
     cudaLaunchAttribute attr[1];

@@ -64,6 +64,8 @@ struct Params {
     float *dump_est, *dump_bnd;  // DUMP kernels only (tests): per (row, query) score estimate and error bound, [n][dump_ld]
     uint32_t dump_ld;
     int op_f16;               // 16-bit kernel: operands are fp16 (an fp16 corpus scanned in place) instead of bf16
+    uint32_t *sync;           // pair kernel, optional sibling lockstep: one arrival counter per tile subset (zeroed per launch)
+    uint32_t sync_every;      // ... every this many slabs (0 = off)
 };
 
 
