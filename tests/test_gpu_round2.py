@@ -394,3 +394,37 @@ def test_cta_pairs_fp16_corpus_and_ragged_rows(knn_lib, oracle_mod):
     ix.release()
     oi, os_ = oracle_mod.knn_exact64(rows, q, k, "cosine")
     check_parity(rows, q, k, "cosine", gi, gs, oi, os_)
+
+
+def test_16bit_index_maintenance_keeps_norms_in_step(knn_lib, oracle_mod):
+    """append / update_row / remove_swap on fp16 and bf16 indexes: the per-row |x|^2 array of the in-place tensor pass must
+    follow every mutation (a stale norm would silently mis-rank under cosine / euclidean), and the device generator of bf16
+    rows must equal round-to-nearest-even of the fp32 stream."""
+    from nornicdb_b200.knn import KnnIndex, from_bf16_bits, to_bf16_bits
+    d, k = 64, 8
+    base = oracle_mod.fill_uniform(6000, d, 111)
+    extra = oracle_mod.fill_uniform(3000, d, 112) * 3.0
+    q = oracle_mod.fill_uniform(12, d, 113)
+    for dtype in ("f16", "bf16"):
+        conv = (lambda a: a.astype(np.float16)) if dtype == "f16" else to_bf16_bits
+        wide = (lambda a: a.astype(np.float32)) if dtype == "f16" else from_bf16_bits
+        for metric in ("cosine", "euclidean"):
+            ix = KnnIndex(d, metric=metric, dtype=dtype)
+            ix.upload(conv(base))
+            ix.append(conv(extra))                      # norms of the appended rows
+            ix.update_row(17, conv(extra[5] * 2.0))     # one row rewritten in place
+            ix.remove_swap(100)                         # last row moves into slot 100
+            host = np.concatenate([wide(conv(base)), wide(conv(extra))])
+            host[17] = wide(conv(extra[5] * 2.0))
+            host[100] = host[-1]
+            host = host[:-1]
+            gi, gs = ix.search(q, k)                    # Q >= 5: the 16-bit tensor pass
+            assert ix.last_path() == "shadow"
+            ix.release()
+            oi, os_ = oracle_mod.knn_exact64(host, q, k, metric)
+            check_parity(host, q, k, metric, gi, gs, oi, os_)
+    ix = KnnIndex(d, metric="dot", dtype="bf16")
+    ix.fill_uniform(4000, 42)
+    got = ix.read_rows(0, 4000)
+    ix.release()
+    assert (got == to_bf16_bits(oracle_mod.fill_uniform(4000, d, 42))).all()
