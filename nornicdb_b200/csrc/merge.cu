@@ -33,7 +33,7 @@ struct MergeParams {
 // the best k at the front after every round.  Keys below the current k-th best are dropped on load.
 __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(MergeParams p) {
     if (p.only_if && *p.only_if == 0) return;
-    __shared__ uint64_t sbuf[MERGE_P];
+    __shared__ uint64_t sbuf[2 * MERGE_P];  // sort buffer (MERGE_P wide); the pre-filter caches up to 2 * MERGE_P whole keys here
     __shared__ int s_fill;
     const uint32_t q = blockIdx.x;
     const uint64_t *base = p.keys + (size_t)q * p.q_stride;
@@ -59,6 +59,122 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(MergeParams p
         __syncthreads();
     }
 
+    // ---- pre-filter (many more keys than k, e.g. the 391 per-CTA lists of a small-shard CUDA-core scan): radix-select the
+    // k-th largest SCORE WORD over all keys first (score words cached in shared memory, 8 bits per pass), so that only the k
+    // best (+ ties) go through the sort — a 2048-wide bitonic network for k = 10 was most of a configs[0] search.
+    uint64_t kth = 0;  // current k-th best key (0 = none yet): keys <= kth are dropped on load
+    __shared__ int m_hist[256];
+    __shared__ uint32_t m_prefix, m_red[2][MERGE_THREADS / 32];
+    __shared__ int m_krem;
+    if (total >= 4ull * p.k && total > 512 && total <= 2ull * MERGE_P) {
+        const int n = (int)total, lane = tid & 31, warp = tid >> 5;
+        uint32_t umax = 0u, umin = 0xffffffffu;
+        for (int i0 = tid; i0 < n; i0 += 4 * MERGE_THREADS) {
+            uint64_t h[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * MERGE_THREADS;
+                const uint32_t l = (uint32_t)(i / (int)p.list_len), sl = (uint32_t)(i - (int)(l * p.list_len));
+                h[u] = i < n ? __ldcg(base + (size_t)l * p.list_stride + sl) : 0ull;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * MERGE_THREADS;
+                if (i < n) { sbuf[i] = h[u]; umax = max(umax, (uint32_t)(h[u] >> 32)); if (h[u]) umin = min(umin, (uint32_t)(h[u] >> 32)); }  // (empty slots stay out of the digit range: fewer passes)
+            }
+        }
+        umax = __reduce_max_sync(0xffffffffu, umax);
+        umin = __reduce_min_sync(0xffffffffu, umin);
+        if (lane == 0) { m_red[0][warp] = umax; m_red[1][warp] = umin; }
+        if (tid == 0) m_krem = (int)p.k;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < MERGE_THREADS / 32; ++w) { umax = max(umax, m_red[0][w]); umin = min(umin, m_red[1][w]); }
+        int rem = 32 - __clz(umax ^ umin);
+        if (tid == 0) m_prefix = rem >= 32 ? 0u : (umax >> rem) << rem;
+        __syncthreads();
+        while (rem > 0) {
+            const int w = rem < 8 ? rem : 8, shift = rem - w;
+            m_hist[tid] = 0;  // MERGE_THREADS == 256
+            __syncthreads();
+            const uint32_t prefix = m_prefix;
+            for (int i = tid; i < n; i += MERGE_THREADS) {
+                const uint32_t hi = (uint32_t)(sbuf[i] >> 32);
+                if (rem >= 32 || (hi >> rem) == (prefix >> rem)) atomicAdd(&m_hist[(hi >> shift) & ((1u << w) - 1u)], 1);
+            }
+            __syncthreads();
+            if (warp == 0) {  // digit holding the krem-th largest: lane l owns the 8 digits below nb - 8l, descending
+                const int krem = m_krem, nb = 1 << w;
+                int loc[8], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int dgt = nb - 1 - (lane * 8 + j);
+                    loc[j] = dgt >= 0 ? m_hist[dgt] : 0;
+                    sum += loc[j];
+                }
+                __syncwarp();
+                int incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                int c = incl - sum;
+                if (c < krem && incl >= krem) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (c + loc[j] >= krem) {
+                            m_prefix = prefix | ((uint32_t)(nb - 1 - (lane * 8 + j)) << shift);
+                            m_krem = krem - c;
+                            break;
+                        }
+                        c += loc[j];
+                    }
+                }
+            }
+            __syncthreads();
+            rem = shift;
+        }
+        const uint32_t kth_hi = m_prefix;  // the k-th largest score word: keys with a smaller one cannot be in the top k
+        if (kth_hi) kth = ((uint64_t)kth_hi << 32) - 1ull;
+        // compact the survivors to the front of the buffer IN PLACE (every thread holds its keys in registers across the
+        // barrier), sort just those, write the result: no second pass over the lists
+        uint64_t mine[2 * MERGE_P / MERGE_THREADS];
+#pragma unroll
+        for (int u = 0; u < 2 * MERGE_P / MERGE_THREADS; ++u) {
+            const int i = tid + u * MERGE_THREADS;
+            mine[u] = i < n ? sbuf[i] : 0ull;
+        }
+        if (tid == 0) s_fill = 0;
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 2 * MERGE_P / MERGE_THREADS; ++u)
+            if (mine[u] > kth) {
+                const int slot = atomicAdd(&s_fill, 1);
+                if (slot < MERGE_P) sbuf[slot] = mine[u];
+            }
+        __syncthreads();
+        if (s_fill <= MERGE_P) {  // (more than MERGE_P keys tie on the k-th score word: take the general path below)
+            const int filled = s_fill;
+            int Ps = 32;
+            while (Ps < filled) Ps <<= 1;
+            for (int i = filled + tid; i < Ps; i += MERGE_THREADS) sbuf[i] = 0ull;
+            block_bitonic_sort_desc(sbuf, Ps);
+            for (uint32_t i = tid; i < p.k; i += MERGE_THREADS) {
+                const uint64_t key = (int)i < filled ? sbuf[i] : 0ull;
+                if (p.out) p.out[(size_t)q * p.k + i] = key;
+                if (p.dec_idx) {
+                    float sc = key_score(key);
+                    if (p.dec_metric == NK_METRIC_EUCLIDEAN) sc = sqrtf(fmaxf(-sc, 0.0f));
+                    p.dec_idx[(size_t)q * p.k + i] = key ? key_row(key) : 0xffffffffu;
+                    p.dec_score[(size_t)q * p.k + i] = key ? sc : 0.0f;
+                }
+            }
+            return;
+        }
+        __syncthreads();
+    }
+
     // sort width: the whole input when it fits a smaller power of two (cross-GPU merges fold a few dozen keys)
     int P = MERGE_P;
     if (total <= (uint64_t)MERGE_P) {
@@ -69,7 +185,6 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(MergeParams p
     if (tid == 0) s_fill = 0;
     __syncthreads();
 
-    uint64_t kth = 0;  // current k-th best key (0 = none yet)
     uint64_t pos = 0;
     while (pos < total) {
         // fill slots [fill, MERGE_P) with keys that can still matter
@@ -92,8 +207,11 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(MergeParams p
         const int filled = s_fill;
         // sort only when the buffer is nearly full or the input is exhausted
         if (pos >= total || filled > P - MERGE_THREADS) {
-            for (int i = filled + tid; i < P; i += MERGE_THREADS) sbuf[i] = 0ull;
-            block_bitonic_sort_desc(sbuf, P);
+            int Ps = 32;  // sort only as wide as the live keys (a pre-filtered input leaves k + ties of them)
+            while (Ps < filled) Ps <<= 1;
+            if (Ps > P) Ps = P;
+            for (int i = filled + tid; i < Ps; i += MERGE_THREADS) sbuf[i] = 0ull;
+            block_bitonic_sort_desc(sbuf, Ps);
             int keep = filled < (int)p.k ? filled : (int)p.k;
             if (filled >= (int)p.k) kth = sbuf[p.k - 1];
             __syncthreads();

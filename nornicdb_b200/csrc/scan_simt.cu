@@ -391,12 +391,6 @@ int scan_simt(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *
             grid_used = (uint32_t)di.num_sms * (uint32_t)occ;
             if (grid_used > num_iv) grid_used = num_iv;
             if (grid_used > max_grid) grid_used = max_grid;
-            // small shards (a few intervals per CTA at most): keep grid * k within one 2048-wide merge round
-            if (num_iv <= (uint32_t)di.num_sms * 8 && (uint64_t)grid_used * a.k > 2048) {
-                uint32_t cap = 2048 / a.k;
-                if (cap < (uint32_t)di.num_sms) cap = (uint32_t)di.num_sms;
-                if (grid_used > cap) grid_used = cap;
-            }
             if (ws_reserve((void **)&ws.cand, &ws.cand_bytes, (size_t)grid_used * 8 * P * 8)) return -1;
             if (ws_reserve((void **)&ws.partial, &ws.partial_bytes, (size_t)a.Q * grid_used * a.k * 8)) return -1;
         }
