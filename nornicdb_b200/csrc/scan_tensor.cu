@@ -1202,6 +1202,8 @@ static int make_filter_plan(const DeviceInfo &di, const ScanArgs &a, Workspace &
         f.sample = next_pow2(8 * a.k);  // k-th best of the sample = top k/S of the shard: ~8-12% of the rows pass at first
         if (f.sample < 128) f.sample = 128;
         if (f.sample > 2048) f.sample = 2048;
+        const int s_env = tc_env_int("NK_TAU_SAMPLE_S", 0);  // experiments: sample size override (power of two)
+        if (s_env >= 32 && s_env <= 2048) f.sample = next_pow2((uint32_t)s_env);
     }
     f.fsmem = (size_t)FINISH_HI * 4 + (size_t)FINISH_CAP * 16 + (size_t)a.dim * 4;
     f.psmem = (size_t)((a.dim + 3) & ~3u) * 4 + (size_t)f.sample * 8;

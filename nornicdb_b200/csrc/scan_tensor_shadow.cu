@@ -62,6 +62,8 @@ struct __align__(8) Shared {
     float qn[QT_MAX];                              // |q| (1 for cosine)
     float qa[QT_MAX], qb[QT_MAX];                  // bound(row, q) = ra(row) qa[q] + rb(row) qb[q]
     int cnt[QT_MAX];
+    uint32_t ethr[QT_MAX];                         // emission: score-word threshold per query
+    int eoff[QT_MAX + 1];                          // emission: prefix of 32-entry chunk counts
 };
 }  // namespace sb
 
@@ -159,6 +161,16 @@ int build_shadow(const float *rows, uint64_t first, uint64_t count, uint32_t dim
     return 0;
 }
 
+// Debug timeline (NK_TC_DEBUG & 64): per-CTA globaltimer stamps, printed by launch_shadow_pass_t after a synchronize.
+//   [0] entry  [1] set-up done  [2] first accumulator ready  [3] last tile's epilogue done  [4] exit
+//   [5] ns in the prune section (epilogue warp 0)  [6] tile index of the first prune  [7] ns waiting for accumulators
+__device__ unsigned long long g_sb_prof[256][16];  // [8] all warps past the tile loop  [9] warp 0 done emitting  [10] live chunks  [11] entries emitted by warp 0
+__device__ __forceinline__ unsigned long long sb_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+    return t;
+}
+
 template <int QT, bool DUMP>
 __global__ void __launch_bounds__(sb::NTHREADS, 1)
 knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_q, tc::Params p) {
@@ -172,6 +184,8 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
     Shared &sh = *reinterpret_cast<Shared *>(smem_raw + (size_t)C::RING_BYTES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool prof = (p.debug & 64) && blockIdx.x < 256;
+    if (prof && tid == 0) { g_sb_prof[blockIdx.x][0] = sb_now(); g_sb_prof[blockIdx.x][6] = ~0ull; }
     const uint32_t num_tiles = (p.n + ROWS - 1) / ROWS;
     // query groups: CTA b serves query block (b % G) over the tile subset (b / G); siblings share tiles through L2
     const uint32_t grp = blockIdx.x % p.qgroups, sub = blockIdx.x / p.qgroups, sgrid = gridDim.x / p.qgroups;
@@ -213,6 +227,7 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
     ptx::tc_fence_after();
     const uint32_t tmem = sh.tmem_base;
     const bool flood = !p.presampled;  // first two tiles: every (row, query) pair is placed directly
+    if (prof && tid == 0) g_sb_prof[blockIdx.x][1] = sb_now();
 
     if (warp == 0) {
         // ===================================== TMA producer: shadow slabs =========================
@@ -284,8 +299,10 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
         // end of the launch needs no selection and the finish step reads short lists (small shards: 26 tiles per CTA at
         // N = 1M would otherwise never prune at all).
         const int prune_at = PB - ROWS;
-        const int prune_trigger = min(prune_at, max(256, 4 * (int)p.k));
+        const int prune_trigger = p.prune_trigger > 0 ? min(prune_at, p.prune_trigger) : min(prune_at, max(192, 4 * (int)p.k));  // (192 / 256 / 384 measured at k = 10: 0.445 / 0.448 / 0.476 ms per 1.25M-row search)
         const bool cosine = p.metric == NK_METRIC_COSINE, euclid = p.metric == NK_METRIC_EUCLIDEAN;
+        const bool eprof = prof && ewarp == 0 && lane == 0;
+        unsigned long long t_prune = 0, t_wait = 0, t_a = 0;
         uint32_t it = 0;
         for (uint32_t tile = sub; tile < num_tiles; tile += sgrid, ++it) {
             const uint32_t buf = it & 1;
@@ -310,8 +327,14 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
                 atomicMax(&sh.max_ra, __float_as_uint(ra));
                 if (!cosine) { atomicMax(&sh.max_rb, __float_as_uint(rb)); atomicMax(&sh.maxxx, __float_as_uint(x2)); }
             }
+            if (eprof) t_a = sb_now();
             ptx::mbar_wait(&sh.accfull[buf], (it >> 1) & 1);
             ptx::tc_fence_after();
+            if (eprof) {
+                const unsigned long long t = sb_now();
+                t_wait += t - t_a;
+                if (it == 0) g_sb_prof[blockIdx.x][2] = t;
+            }
 #pragma unroll 1
             for (uint32_t chunk = 0; chunk < QT / 64; ++chunk) {
                 const uint32_t cb = chunk * 64;
@@ -402,25 +425,38 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
             }
             // prune any buffer that could overflow during the next tile (8 warps, different queries concurrently)
             group_sync(EPI_BAR, EPI_NT);  // every push of this tile is visible
+            if (eprof) t_a = sb_now();
             for (uint32_t qi = ewarp; qi < nq; qi += EPI_WARPS)
                 if (sh.cnt[qi] > prune_trigger) {
+                    if (eprof && g_sb_prof[blockIdx.x][6] == ~0ull) g_sb_prof[blockIdx.x][6] = it;
                     const float margin2 = bf16_margin2(p.metric, __uint_as_float(sh.max_ra), cosine ? 1.0f : __uint_as_float(sh.max_rb),
                                                        __uint_as_float(sh.maxxx), sh.qa[qi], sh.qb[qi], sh.qn[qi]);
                     float floor_tau = p.min_score;
                     const uint32_t gt = __ldcg(p.gtau + q0 + qi);
                     if (gt) floor_tau = fmaxf(floor_tau, ord_to_float(gt));
-                    warp_prune<PRUNE_LANE>(my_cand + (size_t)qi * PB, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, true, margin2, prune_at, floor_tau,
-                                   nullptr, p.flags + FLAG_OVERFLOW);
+                    // the select's cost is the register-resident key count: an early-trigger prune holds ~260-300 keys, not PB
+                    const int have = sh.cnt[qi];
+                    if (have <= 320)
+                        warp_prune<10>(my_cand + (size_t)qi * PB, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, true, margin2, prune_at, floor_tau,
+                                       nullptr, p.flags + FLAG_OVERFLOW);
+                    else if (have <= 512)
+                        warp_prune<16>(my_cand + (size_t)qi * PB, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, true, margin2, prune_at, floor_tau,
+                                       nullptr, p.flags + FLAG_OVERFLOW);
+                    else
+                        warp_prune<PRUNE_LANE>(my_cand + (size_t)qi * PB, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, true, margin2, prune_at, floor_tau,
+                                               nullptr, p.flags + FLAG_OVERFLOW);
                     // everything inside the margin must fit below prune_at, or the next tile could overflow the buffer
                     if (lane == 0 && sh.cnt[qi] >= prune_at) atomicOr(p.flags + FLAG_OVERFLOW, 1);
                     if (lane == 0 && sh.tau[qi] > -INFINITY) atomicMax(p.gtau + q0 + qi, ord_bits(sh.tau[qi]));
                 }
             group_sync(EPI_BAR, EPI_NT);
+            if (eprof) t_prune += sb_now() - t_a;
             for (uint32_t qi = tid - EPI_WARP0 * 32; qi < nq; qi += EPI_NT) {  // adopt the shared thresholds
                 const uint32_t gt = __ldcg(p.gtau + q0 + qi);
                 if (gt) sh.tau[qi] = fmaxf(sh.tau[qi], ord_to_float(gt));
             }
         }
+        if (eprof) { g_sb_prof[blockIdx.x][3] = sb_now(); g_sb_prof[blockIdx.x][5] = t_prune; g_sb_prof[blockIdx.x][7] = t_wait; }
     }
 
     // ---- emit: everything inside this CTA's margin AND above the shared threshold goes to the query's shared list.
@@ -428,15 +464,121 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
     {
         const bool cosine = p.metric == NK_METRIC_COSINE;
         uint64_t *my_cand = p.cand + (size_t)blockIdx.x * QT * PB;
-        for (uint32_t qi = warp; qi < nq; qi += NTHREADS / 32) {
+        // Fast path (buffers with <= k_emit entries, i.e. almost always all of them): no selection, the finish kernel selects
+        // globally — append what still reaches the current threshold.  The buffers live in global memory (L2); walking them
+        // query by query was a chain of dependent round trips (~19 us at the end of every launch, measured).  Instead: the
+        // thresholds of all queries in one round, then the live 32-entry chunks of ALL buffers as one flat work list, 16
+        // independent loads in flight per warp, then the list-fill atomics of the whole batch in one more round.
+        constexpr int NW = NTHREADS / 32, JQ = (QT + NW - 1) / NW;
+        constexpr int STAGE_CHUNKS = Cfg<QT>::RING_BYTES / 256;  // 32-key chunks the (contiguous) operand rings hold
+        if (prof && tid == 0) g_sb_prof[blockIdx.x][8] = sb_now();
+        int n_emitted = 0;
+        if (tid < QT) {
+            // (the shared threshold is fetched asynchronously: its round trip — several microseconds while the other CTAs
+            // still stream — overlaps the staging of the buffers below instead of preceding it)
+            int chunks = 0;
+            sh.ethr[tid] = 0u;
+            if ((uint32_t)tid < nq && sh.cnt[tid] <= (int)p.k_emit) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(ptx::smem_u32(&sh.ethr[tid])), "l"(p.gtau + q0 + tid) : "memory");
+                chunks = (sh.cnt[tid] + 31) >> 5;
+            }
+            sh.eoff[tid + 1] = chunks;
+        }
+        __syncthreads();
+        if (warp == 0) {  // inclusive prefix of the chunk counts -> eoff[q + 1]; eoff[0] = 0
+            constexpr int PERL = QT / 32;
+            int loc[PERL], sum = 0;
+#pragma unroll
+            for (int i = 0; i < PERL; ++i) { loc[i] = sh.eoff[lane * PERL + i + 1]; sum += loc[i]; }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            int run = incl - sum;
+            if (lane == 0) sh.eoff[0] = 0;
+#pragma unroll
+            for (int i = 0; i < PERL; ++i) { run += loc[i]; sh.eoff[lane * PERL + i + 1] = run; }
+        }
+        __syncthreads();
+        {
+            // The operand rings are idle now (every MMA has completed: the epilogue saw the last accumulator): stage the live
+            // chunks there with asynchronous copies — every load of the warp in flight at once, no registers held.  Chunk
+            // c of query q lands in stage slot eoff[q] + c; queries whose chunks do not fit the rings take the per-query path.
+            if (prof && tid == 0) g_sb_prof[blockIdx.x][12] = sb_now();  // prefix done
+            uint64_t *stage = reinterpret_cast<uint64_t *>(a_base);
+            for (uint32_t qi = warp; qi < nq; qi += NW) {
+                const int c0 = sh.eoff[qi], c1 = sh.eoff[qi + 1], n = sh.cnt[qi];
+                if (c1 > STAGE_CHUNKS) continue;
+                for (int ch = 0; ch < c1 - c0; ++ch) {
+                    const int slot = (ch << 5) + lane;
+                    uint64_t *dst = stage + ((size_t)(c0 + ch) << 5) + lane;
+                    if (slot < n)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(ptx::smem_u32(dst)), "l"(my_cand + (size_t)qi * PB + slot) : "memory");
+                    else
+                        *dst = 0ull;
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            if (tid < QT) {  // the shared thresholds have landed too -> final score-word threshold per query
+                float t = fmaxf(sh.tau[tid], p.min_score);
+                const uint32_t gt = sh.ethr[tid];
+                if (gt) t = fmaxf(t, ord_to_float(gt));
+                sh.ethr[tid] = t > -INFINITY ? ord_bits(t) : 0u;
+            }
+            __syncthreads();
+            if (prof && tid == 0) g_sb_prof[blockIdx.x][13] = sb_now();  // staged
+            // survivors per query (pass A), ONE list-fill atomic per query — lane j owns the warp's j-th query, all of them
+            // in one round trip — then the stores (pass B)
+            int my = 0;
+#pragma unroll
+            for (int j = 0; j < JQ; ++j) {
+                const uint32_t qi = warp + j * NW;
+                if (qi >= nq) continue;
+                const int c0 = sh.eoff[qi], c1 = sh.eoff[qi + 1];
+                if (c1 > STAGE_CHUNKS) continue;
+                const uint32_t th = sh.ethr[qi];
+                int tot = 0;
+                for (int c = c0; c < c1; ++c) {
+                    const uint64_t v = stage[((size_t)c << 5) + lane];
+                    tot += __popc(__ballot_sync(0xffffffffu, v != 0ull && (uint32_t)(v >> 32) >= th));
+                }
+                if (lane == j) my = tot;
+            }
+            int off = 0;
+            if (my > 0) off = atomicAdd(p.gcount + q0 + warp + lane * NW, my);
+            if (prof && tid == 0) g_sb_prof[blockIdx.x][14] = sb_now() + (off & 0);  // list-fill atomics answered
+#pragma unroll
+            for (int j = 0; j < JQ; ++j) {
+                const uint32_t qi = warp + j * NW;
+                int goff = __shfl_sync(0xffffffffu, off, j);
+                if (qi >= nq) continue;
+                const int c0 = sh.eoff[qi], c1 = sh.eoff[qi + 1];
+                if (c1 > STAGE_CHUNKS) continue;
+                const uint32_t th = sh.ethr[qi];
+                uint64_t *out = p.partial + (size_t)(q0 + qi) * p.list_cap;
+                for (int c = c0; c < c1; ++c) {
+                    const uint64_t v = stage[((size_t)c << 5) + lane];
+                    const bool keep = v != 0ull && (uint32_t)(v >> 32) >= th;
+                    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+                    const int pos = goff + __popc(m & ((1u << lane) - 1u));
+                    if (keep && pos < (int)p.list_cap) out[pos] = v;
+                    goff += __popc(m);
+                    n_emitted += __popc(m);
+                }
+            }
+            if (prof && tid == 0) { g_sb_prof[blockIdx.x][9] = sb_now(); g_sb_prof[blockIdx.x][10] = (unsigned long long)sh.eoff[QT]; g_sb_prof[blockIdx.x][11] = (unsigned long long)n_emitted; }
+        }
+        for (uint32_t qi = warp; qi < nq; qi += NW) {  // buffers beyond k_emit (near-tie data): select, then emit
+            if (sh.cnt[qi] <= (int)p.k_emit && sh.eoff[qi + 1] <= STAGE_CHUNKS) continue;
             const float margin2 = bf16_margin2(p.metric, __uint_as_float(sh.max_ra), cosine ? 1.0f : __uint_as_float(sh.max_rb),
                                                __uint_as_float(sh.maxxx), sh.qa[qi], sh.qb[qi], sh.qn[qi]);
             float floor_tau = p.min_score;
             const uint32_t gt = __ldcg(p.gtau + q0 + qi);
             if (gt) floor_tau = fmaxf(floor_tau, ord_to_float(gt));
-            if (sh.cnt[qi] <= (int)p.k_emit) {
-                // few entries: no local selection (the finish kernel selects globally) — append what still reaches the
-                // current threshold
+            if (sh.cnt[qi] <= (int)p.k_emit) {  // (did not fit the staging area)
                 const float t = fmaxf(sh.tau[qi], floor_tau);
                 uint64_t thr = t > -INFINITY ? (uint64_t)ord_bits(t) << 32 : 1ull;
                 if (thr == 0ull) thr = 1ull;
@@ -459,6 +601,37 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 2) ptx::tmem_dealloc(tmem, TMEM_COLS);
+    if (prof && tid == 0) g_sb_prof[blockIdx.x][4] = sb_now();
+}
+
+static void sb_print_prof(cudaStream_t stream, uint32_t grid) {
+    static unsigned long long h[256][16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpyFromSymbol(h, g_sb_prof, sizeof(h));
+    const uint32_t g = grid < 256 ? grid : 256;
+    unsigned long long t0 = ~0ull, tend_min = ~0ull, tend_max = 0, e3_max = 0;
+    double setup = 0, first = 0, prune = 0, wait = 0, ends = 0, e3 = 0, ftile = 0;
+    for (uint32_t b = 0; b < g; ++b) t0 = h[b][0] < t0 ? h[b][0] : t0;
+    unsigned long long start_max = 0;
+    for (uint32_t b = 0; b < g; ++b) {
+        start_max = h[b][0] - t0 > start_max ? h[b][0] - t0 : start_max;
+        setup += (double)(h[b][1] - h[b][0]); first += (double)(h[b][2] - h[b][0]); prune += (double)h[b][5]; wait += (double)h[b][7];
+        ends += (double)(h[b][4] - t0); e3 += (double)(h[b][3] - t0); ftile += h[b][6] == ~0ull ? -1.0 : (double)h[b][6];
+        tend_min = h[b][4] - t0 < tend_min ? h[b][4] - t0 : tend_min;
+        tend_max = h[b][4] - t0 > tend_max ? h[b][4] - t0 : tend_max;
+        e3_max = h[b][3] - t0 > e3_max ? h[b][3] - t0 : e3_max;
+    }
+    double sync_at = 0, emit_at = 0, chunks = 0, emitted = 0;
+    for (uint32_t b = 0; b < g; ++b) { sync_at += (double)(h[b][8] - t0); emit_at += (double)(h[b][9] - t0); chunks += (double)h[b][10]; emitted += (double)h[b][11]; }
+    double t12 = 0, t13 = 0, t14 = 0;
+    for (uint32_t b = 0; b < g; ++b) { t12 += (double)(h[b][12] - t0); t13 += (double)(h[b][13] - t0); t14 += (double)(h[b][14] - t0); }
+    fprintf(stderr, "[shadow prof] emission of warp 0: thresholds + prefix +%.1f | staged +%.1f | atomics answered +%.1f\n", t12 / g / 1e3, t13 / g / 1e3, t14 / g / 1e3);
+    fprintf(stderr, "[shadow prof] all warps past the loop avg +%.1f | warp 0 emitted avg +%.1f | live chunks per CTA %.1f | entries emitted by warp 0 %.1f\n",
+            sync_at / g / 1e3, emit_at / g / 1e3, chunks / g, emitted / g);
+    fprintf(stderr, "[shadow prof, %u CTAs] span %.1f us | last CTA start +%.1f | set-up %.1f | first accumulator +%.1f | epilogue done avg +%.1f max +%.1f | "
+            "exit min +%.1f avg +%.1f max +%.1f | prune section %.1f us (first at tile %.1f) | accumulator wait %.1f us\n",
+            g, tend_max / 1e3, start_max / 1e3, setup / g / 1e3, first / g / 1e3, e3 / g / 1e3, e3_max / 1e3, tend_min / 1e3, ends / g / 1e3,
+            tend_max / 1e3, prune / g / 1e3, ftile / g, wait / g / 1e3);
 }
 
 // The 16-bit pass needs a 16-bit image of the rows: the BF16 shadow of an fp32 shard, or — fp16 / bf16 corpora — the rows
@@ -503,11 +676,13 @@ static int launch_shadow_pass_t(const DeviceInfo &di, const ScanArgs &a, Workspa
     p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = nullptr; p.debug = tc_debug_flags(); p.mask = a.row_mask;
     p.gtau = reinterpret_cast<uint32_t *>(ws.keys2); p.gcount = reinterpret_cast<int *>(ws.keys2) + (sp.Qpad + QT_BIG);
     p.presampled = sp.presampled; p.min_score = a.min_score; p.op_f16 = a.dtype == NK_DTYPE_F16;
+    p.prune_trigger = tc_env_int("NK_PRUNE_TRIGGER", 0);
     p.dump_est = sp.dump_est; p.dump_bnd = sp.dump_bnd; p.dump_ld = sp.dump_ld;
     knn_scan_shadow_kernel<QT, DUMP><<<sp.grid, NTHREADS, smem, a.stream>>>(*map_rows, *map_q, p);
     NK_CUDA_OK(cudaGetLastError());
     if (launches) ++*launches;
     if (a.main_launches) ++*a.main_launches;
+    if (p.debug & 64) sb_print_prof(a.stream, sp.grid);
     return 0;
 }
 

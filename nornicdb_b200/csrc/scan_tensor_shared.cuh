@@ -57,6 +57,7 @@ struct Params {
     const int *only_if;       // exact fallback: run only if *only_if != 0
     const uint32_t *mask;     // row bitmask (bit set = row takes part) or nullptr
     int debug;                // NK_TC_DEBUG bit 64: clock64 wait-time instrumentation of CTA 0
+    int prune_trigger;        // 16-bit pass: early prune trigger override (NK_PRUNE_TRIGGER, 0 = default)
     int presampled;           // filter: gtau[] already holds a sampled lower bound of every query's k-th best score
                               // (filter_prep_kernel): no flood tiles, thresholds are adopted at kernel start
     float min_score;          // filter: caller's score floor (VectorIndex minSimilarity, vector_index.go:339-352): rows
