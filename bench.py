@@ -720,7 +720,8 @@ def main():
         c = ix.debug_counters()
         searches = max(ix.stats()["searches"], 1)
         line["filter_retries"] = {"bf16_stage_retry_rate": c["bf16_stage_retries"] / searches, "exact_stage_rate": c["exact_stage_runs"] / searches,
-                                  "searches": searches, "longest_survivor_list_last_search": c["longest_list"], "overflow_bits": c["overflow_bits"]}
+                                  "searches": searches, "longest_survivor_list_last_search": c["longest_list"], "overflow_bits": c["overflow_bits"],
+                                  "note": "asynchronous API: a first-stage overflow goes straight to the exact stage (exact_stage_rate); the TF32 retry stage belongs to the host-synchronous nk_search"}
     if not args.no_parity:
         line["parity_check"] = parity_check(run, ix, lo, hi, N_total, dim, dtype, Q, k, metric, res, clustered=clustered)
     for key in ("out_idx", "out_score", "q_all", "search_dev"):

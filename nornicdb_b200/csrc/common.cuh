@@ -35,6 +35,28 @@ void clear_error();
 
 // Every entry point binds the device it needs (cudaSetDevice per call, so callers may hop OS threads) and puts the caller's
 // current device back on return: hosts that track the current device themselves (PyTorch, CuPy) never see it move.
+// ---- programmatic dependent launch (sm_90+): a kernel launched through launch_pdl() may be scheduled while the kernel
+// before it in the stream is still running; pdl_wait() — the first statement of every such kernel — blocks until that
+// kernel has completed and its memory is visible (a no-op for an ordinary launch), pdl_trigger() lets the NEXT kernel's
+// launch start early.  Used for the short, dependent launches of one search (finish, the early-exit retry stages, the
+// cross-GPU push and merge): their launch latency, ~2 us each, overlaps the predecessor instead of following it.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();  // NK_PDL (default 1), read once
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool dependent, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (dependent && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 struct DeviceGuard {
     int prev = -1;
     DeviceGuard() {

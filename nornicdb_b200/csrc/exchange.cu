@@ -42,6 +42,8 @@ struct PushParams {
 };
 
 __global__ void exchange_push_kernel(PushParams p) {
+    pdl_trigger();
+    pdl_wait();  // programmatic dependent of the kernel that produced p.keys (common.cuh)
     unsigned char *dst_base = p.peer[blockIdx.x];
     uint64_t *dst = reinterpret_cast<uint64_t *>(dst_base + p.data_off);
     for (uint32_t i = threadIdx.x; i < p.n_keys; i += blockDim.x) dst[i] = p.keys[i];
@@ -183,8 +185,7 @@ int nk_comm_exchange_merge(NkComm *c, const uint64_t *keys_dev, uint32_t Q, uint
     for (int r = 0; r < c->world; ++r) p.peer[r] = c->peer[r];
     p.data_off = c->flag_bytes + ((size_t)parity * c->world + c->rank) * c->slot_bytes;
     p.flag_off = ((size_t)parity * c->world + c->rank) * 4;
-    nk::exchange_push_kernel<<<c->world, 256, 0, st>>>(p);
-    NK_CUDA_OK(cudaGetLastError());
+    NK_CUDA_OK(nk::launch_pdl(nk::exchange_push_kernel, dim3(c->world), dim3(256), 0, st, true, p));
     const uint64_t *lists = reinterpret_cast<const uint64_t *>(c->local + c->flag_bytes + (size_t)parity * c->world * c->slot_bytes);
     const uint32_t *flags = reinterpret_cast<const uint32_t *>(c->local) + (size_t)parity * c->world;
     return nk::merge_keys(lists, (uint32_t)c->world, c->slot_bytes / 8, k, Q, k, nullptr, st, nullptr, 0, out_idx_dev, out_score_dev, metric,

@@ -32,6 +32,8 @@ struct MergeParams {
 // One CTA per query.  Streams the n_lists*k candidate keys through a 2048-wide sort buffer, keeping
 // the best k at the front after every round.  Keys below the current k-th best are dropped on load.
 __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(MergeParams p) {
+    pdl_trigger();
+    pdl_wait();  // programmatic dependent of the scan / push kernel before it (common.cuh)
     if (p.only_if && *p.only_if == 0) return;
     __shared__ uint64_t sbuf[2 * MERGE_P];  // sort buffer (MERGE_P wide); the pre-filter caches up to 2 * MERGE_P whole keys here
     __shared__ int s_fill;
@@ -248,8 +250,7 @@ int merge_keys(const uint64_t *keys, uint32_t n_lists, size_t list_stride, size_
     }
     MergeParams p{keys, n_lists, list_stride, q_stride, k, out_keys, only_if, list_len ? list_len : k, dec_idx, dec_score, dec_metric,
                   wait_flags, wait_epoch, wait_err};
-    merge_keys_kernel<<<Q, MERGE_THREADS, 0, stream>>>(p);
-    NK_CUDA_OK(cudaGetLastError());
+    NK_CUDA_OK(launch_pdl(merge_keys_kernel, dim3(Q), dim3(MERGE_THREADS), 0, stream, true, p));
     return 0;
 }
 

@@ -1,5 +1,6 @@
 // runtime.cu — error state, device info and grow-only workspaces.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -29,6 +30,13 @@ const char *get_error() {
     std::lock_guard<std::mutex> lk(g_last_mu);
     memcpy(g_ret, g_last, sizeof(g_ret));  // a stable per-thread copy: the caller reads it after the lock is gone
     return g_ret;
+}
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("NK_PDL");
+        return e ? atoi(e) != 0 : true;
+    }();
+    return on;
 }
 void clear_error() {
     g_err[0] = 0;

@@ -118,6 +118,8 @@ __device__ __forceinline__ void warp_reduce_scatter(float (&v)[V], int lane) {
 
 template <typename T, bool VEC, int QT, int R, bool EUCLID>
 __global__ void __launch_bounds__(SIMT_THREADS) knn_scan_simt_kernel(SimtParams p) {
+    pdl_trigger();  // the merge launch behind this scan may begin (it waits for this grid before reading)
+    pdl_wait();     // exact-stage twin of a filter search: programmatic dependent of the finish kernel
     if (p.only_if && *p.only_if == 0) return;
     using L = Lane<T, VEC>;
     constexpr int EPL = L::EPL;
@@ -398,8 +400,7 @@ int scan_simt(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, uint64_t *
         p.rows = a.rows; p.n = a.n; p.dim = a.dim; p.row_base = a.row_base;
         p.queries = a.queries; p.q0 = q0; p.nq = left < (uint32_t)qt ? left : (uint32_t)qt; p.k = a.k;
         p.metric = a.metric; p.P = P; p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.only_if = a.only_if; p.below = a.below; p.mask = a.row_mask; p.min_score = a.min_score;
-        kern<<<grid_used, SIMT_THREADS, smem, a.stream>>>(p);
-        NK_CUDA_OK(cudaGetLastError());
+        NK_CUDA_OK(launch_pdl(kern, dim3(grid_used), dim3(SIMT_THREADS), smem, a.stream, a.only_if != nullptr && !a.defer_tail, p));
         if (launches) ++*launches;
         if (a.main_launches) ++*a.main_launches;
         q0 += p.nq;

@@ -346,6 +346,8 @@ knn_scan_tc_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_co
     using C = Cfg<NT, QT>;
     constexpr bool FILTER = NT == 1;
     constexpr int A_COL = C::A_COL, B_BYTES = C::B_BYTES;
+    pdl_trigger();
+    pdl_wait();
     if (p.only_if && *p.only_if == 0) return;  // exact fallback not needed (uniform over the grid)
 
     extern __shared__ unsigned char smem_dyn[];
@@ -777,6 +779,8 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
     float *qs = reinterpret_cast<float *>(smem_raw + FINISH_HI * 4 + FINISH_CAP * 16);        // query
     __shared__ float s_qq;
     __shared__ int s_count, s_last;
+    pdl_trigger();
+    pdl_wait();  // launched as a programmatic dependent of the scan (common.cuh)
     if (p.only_if && *p.only_if == 0) return;
     const uint32_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1120,8 +1124,10 @@ static int launch_pass(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, c
     p.gtau = reinterpret_cast<uint32_t *>(ws.keys2); p.gcount = reinterpret_cast<int *>(ws.keys2) + (t.Qpad + QT_BIG);
     p.presampled = t.presampled; p.min_score = a.min_score;
     p.dump_est = t.dump_est; p.dump_bnd = t.dump_bnd; p.dump_ld = t.dump_ld;
-    knn_scan_tc_kernel<NT, QT, DUMP><<<t.grid, THREADS, smem, a.stream>>>(*map_rows, *map_qhi, *map_qlo, p);
-    NK_CUDA_OK(cudaGetLastError());
+    // (asynchronous API: the early-exit retry / exact stages are programmatic dependents — their launch overlaps the kernel
+    // before them.  Not for the host-synchronous API: measured 5-15 us slower per nk_search, the copy-out behind it waits longer)
+    NK_CUDA_OK(launch_pdl(knn_scan_tc_kernel<NT, QT, DUMP>, dim3(t.grid), dim3(THREADS), smem, a.stream, t.only_if != nullptr && !a.defer_tail, *map_rows, *map_qhi,
+                          *map_qlo, p));
     if (launches) ++*launches;
     if (t.count_main && a.main_launches) ++*a.main_launches;
     return 0;
@@ -1301,14 +1307,15 @@ int scan_tensor_filter_tail(const DeviceInfo &di, const ScanArgs &a, Workspace &
     using namespace tc;
     FilterPlan f;
     if (make_filter_plan(di, a, ws, &f)) return -1;
-    if (f.stage2) {
-        // the same search over the fp32 rows with the (much tighter) TF32 margins, if a 16-bit margin buffer overflowed
+    if (f.stage2 && a.defer_tail) {
+        // the same search over the fp32 rows with the (much tighter) TF32 margins, if a 16-bit margin buffer overflowed.
+        // Host-driven tail only: queued blindly (asynchronous API) the stage would cost two early-exit launches on EVERY
+        // search to make the rare overflow cheaper — there an overflow goes straight to the exact stage.
         if (tf32_passes(di, a, ws, f, 0, ws.flags + FLAG_RETRY, false, 0, launches)) return -1;
         FinishParams fp{};
         fill_finish(fp, a, ws, f, out_keys);
         fp.q_big = 0; fp.only_if = ws.flags + FLAG_RETRY; fp.mark_retry = 0;
-        filter_finish_kernel<<<a.Q, FINISH_THREADS, f.fsmem, a.stream>>>(fp);
-        NK_CUDA_OK(cudaGetLastError());
+        NK_CUDA_OK(launch_pdl(filter_finish_kernel, dim3(a.Q), dim3(FINISH_THREADS), f.fsmem, a.stream, !a.defer_tail, fp));
         if (launches) ++*launches;
     }
     ScanArgs b = a;
@@ -1378,9 +1385,8 @@ int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
 
     FinishParams fp{};
     fill_finish(fp, a, ws, f, out_keys);
-    fp.q_big = q_big; fp.only_if = nullptr; fp.mark_retry = f.stage2 ? 1 : 0;
-    filter_finish_kernel<<<a.Q, FINISH_THREADS, f.fsmem, a.stream>>>(fp);
-    NK_CUDA_OK(cudaGetLastError());
+    fp.q_big = q_big; fp.only_if = nullptr; fp.mark_retry = (f.stage2 && a.defer_tail) ? 1 : 0;
+    NK_CUDA_OK(launch_pdl(filter_finish_kernel, dim3(a.Q), dim3(FINISH_THREADS), f.fsmem, a.stream, !a.defer_tail, fp));
     if (launches) ++*launches;
     tc_print_prof(a.stream, f.num_tiles, f.grid, (a.dim + BK - 1) / BK);
     if (a.defer_tail) return 0;

@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(sb::NTHREADS, 1)
 knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_constant__ CUtensorMap map_q, tc::Params p) {
     using namespace sb;
     using C = Cfg<QT>;
+    pdl_trigger();  // the finish kernel's launch may begin now (it waits for this grid's completion before reading anything)
     if (p.only_if && *p.only_if == 0) return;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *smem_raw = smem_dyn + ((1024u - (ptx::smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -426,8 +427,9 @@ knn_scan_shadow_kernel(const __grid_constant__ CUtensorMap map_rows, const __gri
             // prune any buffer that could overflow during the next tile (8 warps, different queries concurrently)
             group_sync(EPI_BAR, EPI_NT);  // every push of this tile is visible
             if (eprof) t_a = sb_now();
+            // (never between the two flood tiles: the second one is placed by slot, behind the first one's 256 entries)
             for (uint32_t qi = ewarp; qi < nq; qi += EPI_WARPS)
-                if (sh.cnt[qi] > prune_trigger) {
+                if (sh.cnt[qi] > prune_trigger && !(flood && it == 0)) {
                     if (eprof && g_sb_prof[blockIdx.x][6] == ~0ull) g_sb_prof[blockIdx.x][6] = it;
                     const float margin2 = bf16_margin2(p.metric, __uint_as_float(sh.max_ra), cosine ? 1.0f : __uint_as_float(sh.max_rb),
                                                        __uint_as_float(sh.maxxx), sh.qa[qi], sh.qb[qi], sh.qn[qi]);

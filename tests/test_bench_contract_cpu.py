@@ -72,6 +72,7 @@ def test_round2_bench_lines_carry_parity_check_and_grid():
         assert "error" not in e, (name, e)
         assert e["ms_per_step"] > 0 and 0 < e["roofline_frac"] < 1.25 and e["bound"] in ("hbm", "tensor")
     assert one["also"]["headline_clustered"]["filter_retries"]["first_stage_retry_rate"] <= 0.05  # the round-1 cliff
+    assert one["also"]["headline_clustered"]["filter_retries"]["exact_stage_rate"] <= 0.05
     st = one["cpu_baseline"]["single_thread"]
     assert st["cores"] == 1 and st["value"] > 0 and one["cpu_baseline"]["value"] >= st["value"] * 0.9
     for name in ("headline_8gpu_peer", "c5_8gpu_peer"):
