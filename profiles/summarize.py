@@ -107,9 +107,6 @@ if __name__ == "__main__":
         (f"launches_{tag}_simt.csv", f"launches_{tag}_c2_simt.md",
          f"Launch list, round {tag[1:]}: bench.py c2 (N=1M d=1024 Q=64 k=10 cosine), CUDA-core path (first working version)"),
     ]
-    for src, dst, title in LAUNCH_LISTS:
-        if os.path.exists(os.path.join(G, src)):
-            launches(os.path.join(G, src), os.path.join(OUT, dst), title)
     N10, D = 10_000_000, 1024
     CAPTURES = [  # (ncu-rep, md, title, algorithmic bytes per launch, traffic.json keys)
         (f"prof_{tag}_shadow_headline.ncu-rep", f"ncu_{tag}_scan_shadow_headline.md",
@@ -138,6 +135,21 @@ if __name__ == "__main__":
             (f"prof_{tag}_finish_headline.ncu-rep", f"ncu_{tag}_filter_finish_headline.md", "filter_finish_kernel — headline", None, []),
             (f"prof_{tag}_prep_headline.ncu-rep", f"ncu_{tag}_filter_prep_headline.md", "filter_prep_kernel — headline", None, []),
         ]
+        N8 = 1_250_000
+        LAUNCH_LISTS.append((f"launches_{tag}_shard.csv", f"launches_{tag}_shard.md",
+                             "Launch list, round 2: one GPU at the 8-GPU shard shape (N=1.25M d=1024 Q=64 k=10 cosine), asynchronous API"))
+        CAPTURES += [
+            (f"prof_{tag}_shadow_shard.ncu-rep", f"ncu_{tag}_scan_shadow_shard.md",
+             "knn_scan_shadow_kernel<64> at the 8-GPU shard shape — N=1.25M d=1024 fp32 Q=64 k=10 cosine (after the emission rework)", N8 * D * 2 + N8 * 8, []),
+            (f"prof_{tag}_finish_shard.ncu-rep", f"ncu_{tag}_filter_finish_shard.md", "filter_finish_kernel — 8-GPU shard shape (a real launch, not the tail's early exit)", None, []),
+            (f"prof_{tag}_prep_shard.ncu-rep", f"ncu_{tag}_filter_prep_shard.md", "filter_prep_kernel — 8-GPU shard shape", None, []),
+        ]
+    only = sys.argv[2] if len(sys.argv) > 2 else ""  # e.g. `summarize.py r2 shard`: only the files whose name contains it
+    LAUNCH_LISTS = [x for x in LAUNCH_LISTS if only in x[0]]
+    CAPTURES = [x for x in CAPTURES if only in x[0]]
+    for src, dst, title in LAUNCH_LISTS:
+        if os.path.exists(os.path.join(G, src)):
+            launches(os.path.join(G, src), os.path.join(OUT, dst), title)
     tpath = os.path.join(OUT, "traffic.json")
     t = json.load(open(tpath)) if os.path.exists(tpath) else {}
     for rep, md, title, algo, keys in CAPTURES:
