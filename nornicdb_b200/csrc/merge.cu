@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_keys_kernel(MergeParams p
         int rem = 32 - __clz(umax ^ umin);
         if (tid == 0) m_prefix = rem >= 32 ? 0u : (umax >> rem) << rem;
         __syncthreads();
-        while (rem > 0) {
+        while (rem > 10) {  // (<= 10 unresolved low bits: the prefix is a lower bound of the k-th score word — a few more keys reach the sort)
             const int w = rem < 8 ? rem : 8, shift = rem - w;
             m_hist[tid] = 0;  // MERGE_THREADS == 256
             __syncthreads();

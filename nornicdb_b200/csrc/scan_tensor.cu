@@ -769,7 +769,17 @@ struct FinishParams {
     int mark_retry;          // first stage of a two-stage filter: overflow -> retry marker + state wipe
     uint32_t *state;         // gtau[QA] + gcount[QA]
     uint32_t state_words;
+    int debug;               // NK_TC_DEBUG & 64: per-CTA phase stamps (g_fin_prof)
 };
+
+// Debug timeline of the finish kernel (NK_TC_DEBUG & 64), printed after the first-stage finish launch:
+//   [0] entry  [1] list cached  [2] k-th bound selected  [3] survivors gathered  [4] re-scored  [5] ranked  [6] exit  [7] list length
+__device__ unsigned long long g_fin_prof[256][8];
+__device__ __forceinline__ unsigned long long fin_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+    return t;
+}
 
 __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -784,6 +794,8 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
     if (p.only_if && *p.only_if == 0) return;
     const uint32_t q = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool prof = p.debug && q < 256 && tid == 0;
+    if (prof) g_fin_prof[q][0] = fin_now();
     for (uint32_t j = tid; j < p.dim; j += FINISH_THREADS) qs[j] = p.queries[(size_t)q * p.dim + j];
     int n = p.gcount[q];
     if (tid == 0) atomicMax(p.flags + FLAG_LONGEST, n);  // diagnostics: longest shared list of this search
@@ -815,6 +827,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
     }
     auto hi_at = [&](int i) -> uint32_t { return cached ? shi[i] : (uint32_t)(__ldcg(list + i) >> 32); };
     __syncthreads();
+    if (prof) { g_fin_prof[q][1] = fin_now(); g_fin_prof[q][7] = (unsigned long long)n; }
     if (warp == 0) {
         float a = 0.0f;
         for (uint32_t j = lane; j < p.dim; j += 32) a = fmaf(qs[j], qs[j], a);
@@ -849,7 +862,10 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
         int rem = 32 - __clz(umax ^ umin);  // low bits in which the bounds differ (0: all equal)
         if (tid == 0) s_prefix = rem >= 32 ? 0u : (umax >> rem) << rem;
         __syncthreads();
-        while (rem > 0) {
+        // The select stops with <= 10 low bits unresolved: the prefix (low bits zero) is then a LOWER bound of the k-th largest
+        // bound, at most 2^10 ulps (~1e-4 relative) below it — far inside the filter margin subtracted next, so at most a
+        // stray extra survivor is re-scored, and two of the four histogram passes (3 barriers of 1024 threads each) are gone.
+        while (rem > 10) {
             const int w = rem < 8 ? rem : 8, shift = rem - w;
             if (tid < 256) hist[tid] = 0;
             __syncthreads();
@@ -905,6 +921,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
     // ---- how many rows are inside the margin?  Almost always a few dozen: ONE gather + re-score round.  Only adversarial
     // near-tie data (thousands of survivors) goes through the list in windows, the running best k carried over.
     const uint32_t thr_hi = (uint32_t)(thr_key >> 32);  // keys >= thr_key  <=>  score word >= thr_hi (thr_key's low word is 0 or 1)
+    if (prof) g_fin_prof[q][2] = fin_now();
     int mine = 0;
     for (int i = tid; i < n; i += FINISH_THREADS) mine += hi_at(i) >= thr_hi ? 1 : 0;
     mine = __reduce_add_sync(0xffffffffu, mine);
@@ -925,6 +942,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
             }
         }
         __syncthreads();
+        if (prof && w0 == 0) g_fin_prof[q][3] = fin_now();
         const int count = s_count;  // <= FINISH_WIN
         for (int i = warp; i < count; i += FINISH_THREADS / 32) {
             const uint32_t grow = key_row(sb[i]);
@@ -934,6 +952,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
         }
         const int total = carry + count;
         __syncthreads();
+        if (prof && w0 == 0) g_fin_prof[q][4] = fin_now();
         if (total <= FINISH_THREADS) {
             // small sets (the common case): rank by counting — one barrier instead of a 15-45 stage bitonic network
             const uint64_t mykey = tid < total ? se[tid] : 0ull;
@@ -953,6 +972,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
         }
         carry = total < (int)p.k ? total : (int)p.k;
     }
+    if (prof) g_fin_prof[q][5] = fin_now();
     for (uint32_t i = tid; i < p.k; i += FINISH_THREADS) {
         const uint64_t key = (int)i < carry ? se[i] : 0ull;
         p.out[(size_t)q * p.k + i] = key;
@@ -970,6 +990,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) filter_finish_kernel(FinishPar
         s_last = atomicAdd(p.flags + FLAG_FINISH_CTAS, 1) == (int)gridDim.x - 1;
     }
     __syncthreads();
+    if (prof) g_fin_prof[q][6] = fin_now();
     if (!s_last) return;
     __threadfence();
     const int ovf = atomicOr(p.flags + FLAG_OVERFLOW, 0);
@@ -1131,6 +1152,24 @@ static int launch_pass(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, c
     if (launches) ++*launches;
     if (t.count_main && a.main_launches) ++*a.main_launches;
     return 0;
+}
+
+static void fin_print_prof(cudaStream_t stream, uint32_t Q) {
+    if (!(tc_debug_flags() & 64)) return;
+    static unsigned long long h[256][8];
+    cudaStreamSynchronize(stream);
+    cudaMemcpyFromSymbol(h, g_fin_prof, sizeof(h));
+    const uint32_t g = Q < 256 ? Q : 256;
+    unsigned long long t0 = ~0ull, tmax = 0;
+    for (uint32_t b = 0; b < g; ++b) { t0 = h[b][0] < t0 ? h[b][0] : t0; tmax = h[b][6] > tmax ? h[b][6] : tmax; }
+    double a[8] = {0};
+    for (uint32_t b = 0; b < g; ++b) {
+        for (int i = 1; i < 7; ++i) a[i] += (double)(h[b][i] - h[b][i - 1]);
+        a[0] += (double)(h[b][0] - t0);
+        a[7] += (double)h[b][7];
+    }
+    fprintf(stderr, "[finish prof, %u CTAs] span %.1f us | entry +%.1f | list cached %.1f | k-th bound %.1f | gather %.1f | re-score %.1f | rank %.1f | write + count %.1f | "
+            "list length %.0f\n", g, (tmax - t0) / 1e3, a[0] / g / 1e3, a[1] / g / 1e3, a[2] / g / 1e3, a[3] / g / 1e3, a[4] / g / 1e3, a[5] / g / 1e3, a[6] / g / 1e3, a[7] / g);
 }
 
 static void tc_print_prof(cudaStream_t stream, uint32_t num_tiles, uint32_t grid, uint32_t nslab) {
@@ -1386,9 +1425,11 @@ int scan_tensor_filter(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, u
     FinishParams fp{};
     fill_finish(fp, a, ws, f, out_keys);
     fp.q_big = q_big; fp.only_if = nullptr; fp.mark_retry = (f.stage2 && a.defer_tail) ? 1 : 0;
+    fp.debug = tc_debug_flags() & 64;
     NK_CUDA_OK(launch_pdl(filter_finish_kernel, dim3(a.Q), dim3(FINISH_THREADS), f.fsmem, a.stream, !a.defer_tail, fp));
     if (launches) ++*launches;
     tc_print_prof(a.stream, f.num_tiles, f.grid, (a.dim + BK - 1) / BK);
+    fin_print_prof(a.stream, a.Q);
     if (a.defer_tail) return 0;
     return scan_tensor_filter_tail(di, a, ws, out_keys, launches);
 }
