@@ -101,3 +101,95 @@ def test_assignment_candidate_rule_contains_the_true_nearest_centroid():
             assert top[0][1] == want
         got = min(cands, key=lambda ci: (-true_s[ci], ci))  # exact re-scoring in ascending order, strict comparison
         assert got == want
+
+
+# ---- the truncated radix select of filter_finish_kernel / merge_keys_kernel (scan_tensor.cu, merge.cu) -----------------
+def _ord_bits(x):
+    """common.cuh ord_bits: order-preserving map float32 -> uint32."""
+    b = np.asarray(x, dtype=np.float32).view(np.uint32)
+    return np.where(b & 0x80000000, ~b, b | 0x80000000).astype(np.uint32)
+
+
+def _device_select(words, k, stop_bits=10):
+    """The kernels' select, statement for statement: common prefix of [umin, umax], then 8-bit histogram passes from the
+    top of the varying bits, stopping once <= stop_bits low bits are unresolved.  Returns the prefix (low bits zero)."""
+    words = np.asarray(words, dtype=np.uint64)
+    umax, umin = int(words.max()), int(words.min())
+    rem = (umax ^ umin).bit_length()                 # 32 - clz
+    prefix = 0 if rem >= 32 else (umax >> rem) << rem
+    krem = k
+    while rem > stop_bits:
+        w = min(rem, 8)
+        shift = rem - w
+        sel = words if rem >= 32 else words[(words >> rem) == (prefix >> rem)]
+        hist = np.bincount(((sel >> shift) & ((1 << w) - 1)).astype(np.int64), minlength=1 << w)
+        c = 0
+        for digit in range((1 << w) - 1, -1, -1):    # the digit holding the krem-th largest
+            if c + hist[digit] >= krem:
+                prefix |= digit << shift
+                krem -= c
+                break
+            c += hist[digit]
+        rem = shift
+    return prefix, rem
+
+
+@pytest.mark.parametrize("case", ["scores", "near_ties", "all_equal", "sign_span", "tiny_range"])
+@pytest.mark.parametrize("k", [1, 10, 100])
+def test_truncated_radix_select_is_a_tight_lower_bound_of_the_kth_largest(case, k):
+    rng = np.random.default_rng(hash((case, k)) & 0xFFFF)
+    n = 3000
+    if case == "scores":
+        x = rng.uniform(0.05, 0.4, n)
+    elif case == "near_ties":
+        x = 0.25 + rng.standard_normal(n) * 1e-6
+    elif case == "all_equal":
+        x = np.full(n, 0.125)
+    elif case == "sign_span":
+        x = rng.uniform(-1.0, 1.0, n)
+    else:
+        x = np.float32(0.3) + np.arange(n, dtype=np.float32) * np.float32(2e-8)
+    words = _ord_bits(x.astype(np.float32))
+    prefix, unresolved = _device_select(words, k)
+    kth = int(np.sort(words)[::-1][k - 1])
+    assert unresolved <= 10
+    assert prefix <= kth                                   # a lower bound: the threshold derived from it is sound
+    assert kth - prefix < (1 << 10)                        # ... and within 2^10 ulps of the exact k-th largest
+    assert int((words >= prefix).sum()) >= k               # at least k entries survive the cut (merge pre-filter)
+    exact, _ = _device_select(words, k, stop_bits=0)       # the untruncated select finds the k-th largest itself
+    assert exact == kth
+
+
+# ---- emission layout of knn_scan_shadow_kernel (scan_tensor_shadow.cu): chunks staged in the operand rings -------------
+@pytest.mark.parametrize("QT,ring_bytes", [(64, 4 * 32768 + 8 * 8192), (128, 4 * 32768 + 5 * 16384)])
+def test_emission_stages_every_live_entry_exactly_once(QT, ring_bytes):
+    rng = np.random.default_rng(QT)
+    NW, k_emit, stage_chunks = 12, 512, ring_bytes // 256
+    for trial in range(50):
+        nq = int(rng.integers(1, QT + 1))
+        cnt = rng.integers(0, 1024, QT)
+        cnt[rng.random(QT) < 0.5] //= 8                    # mostly short buffers, some long, some beyond k_emit
+        chunks = np.where((np.arange(QT) < nq) & (cnt <= k_emit), (cnt + 31) >> 5, 0)
+        eoff = np.concatenate([[0], np.cumsum(chunks)])
+        staged = {}                                        # stage slot -> (query, buffer slot), as the kernel fills them
+        slow = []
+        for warp in range(NW):
+            for qi in range(warp, nq, NW):
+                c0, c1 = int(eoff[qi]), int(eoff[qi + 1])
+                if c1 > stage_chunks:
+                    continue
+                for ch in range(c1 - c0):
+                    for lane in range(32):
+                        slot = ch * 32 + lane
+                        key = (c0 + ch) * 32 + lane
+                        assert key not in staged and key < stage_chunks * 32
+                        staged[key] = (qi, slot) if slot < cnt[qi] else None
+        for qi in range(nq):                               # the per-query path takes exactly the others
+            if not (cnt[qi] <= k_emit and eoff[qi + 1] <= stage_chunks):
+                slow.append(qi)
+        for qi in range(nq):
+            live = {(q, s) for v in staged.values() if v is not None for (q, s) in [v] if q == qi}
+            if qi in slow:
+                assert not live
+            else:
+                assert live == {(qi, s) for s in range(int(cnt[qi]))}
