@@ -334,8 +334,18 @@ knn_scan_pair_kernel(const __grid_constant__ CUtensorMap map_rows, const __grid_
                     float floor_tau = p.min_score;
                     const uint32_t gt = __ldcg(p.gtau + q0 + qi);
                     if (gt) floor_tau = fmaxf(floor_tau, ord_to_float(gt));
-                    warp_prune<PRUNE_LANE>(my_cand + (size_t)qi * PB, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, true, margin2, prune_at,
-                                           floor_tau, nullptr, p.flags + FLAG_OVERFLOW);
+                    // the select's cost is the register-resident key count: size it to what the buffer holds (512 right after
+                    // the flood tiles, 512-700 at a later trigger), not to its 1024 slots
+                    const int have = sh.cnt[qi];
+                    if (have <= 512 && p.prune_trigger != -1)  // (NK_PRUNE_TRIGGER=-1: A/B switch, always the full-width select)
+                        warp_prune<16>(my_cand + (size_t)qi * PB, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, true, margin2, prune_at,
+                                       floor_tau, nullptr, p.flags + FLAG_OVERFLOW);
+                    else if (have <= 704 && p.prune_trigger != -1)
+                        warp_prune<22>(my_cand + (size_t)qi * PB, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, true, margin2, prune_at,
+                                       floor_tau, nullptr, p.flags + FLAG_OVERFLOW);
+                    else
+                        warp_prune<PRUNE_LANE>(my_cand + (size_t)qi * PB, &sh.cnt[qi], &sh.tau[qi], p.k, lane, nullptr, 0, true, margin2, prune_at,
+                                               floor_tau, nullptr, p.flags + FLAG_OVERFLOW);
                     if (lane == 0 && sh.cnt[qi] >= prune_at) atomicOr(p.flags + FLAG_OVERFLOW, 1);
                     if (lane == 0 && sh.tau[qi] > -INFINITY) atomicMax(p.gtau + q0 + qi, ord_bits(sh.tau[qi]));
                 }
@@ -413,6 +423,7 @@ int launch_pair_pass(const DeviceInfo &di, const ScanArgs &a, Workspace &ws, con
     p.cand = ws.cand; p.partial = ws.partial; p.flags = ws.flags; p.mask = a.row_mask;
     p.gtau = reinterpret_cast<uint32_t *>(ws.keys2); p.gcount = reinterpret_cast<int *>(ws.keys2) + (sp.Qpad + QT_BIG);
     p.presampled = 0; p.min_score = a.min_score; p.op_f16 = a.dtype == NK_DTYPE_F16;
+    p.prune_trigger = tc_env_int("NK_PRUNE_TRIGGER", 0);
     p.sync_every = (uint32_t)tc_env_int("NK_PAIR_SYNC", 0);
     if (p.sync_every && sp.qgroups > 1) {
         if (ws_reserve((void **)&ws.below, &ws.below_bytes, 1024)) return -1;  // (the big-k bound array doubles as the counter block)
